@@ -1,0 +1,188 @@
+/* splicedice_b200.h -- C-ABI of the B200-native SpliceDICE hot path.
+ *
+ * One shared library, `libsplicedice_b200.so`, built from splicedice_b200/csrc/ with
+ *   nvcc -gencode arch=compute_100a,code=sm_100a
+ * Plain pointers and sizes only; no C++/torch types cross this boundary, so the
+ * reference (a pure-Python package) binds it with ctypes -- see INTEGRATION.md.
+ *
+ * The reference has no FFI of its own: its hot path is a set of Python methods.
+ * Each entry point below names the reference code it replaces (paths relative to
+ * /root/reference/splicedice/).
+ *
+ * Conventions
+ *   - `*_dev` / unsuffixed compute entry points take DEVICE pointers owned by the
+ *     caller; the library never frees or retains them.  `*_host` entry points take
+ *     HOST pointers and do their own (pipelined) transfers.
+ *   - `stream` is a `cudaStream_t` passed as `void*` (NULL = default stream).  Calls
+ *     are asynchronous on that stream unless stated otherwise.
+ *   - Matrices are row-major [row = junction][col = sample] with a leading dimension
+ *     `ld_*` in ELEMENTS (>= n_samples); the 128-bit fast paths need the base pointer
+ *     16-byte aligned and ld a multiple of 4, otherwise a scalar kernel runs.
+ *   - Every function returns SD_OK (0) or an SD_ERR_* code; `sd_last_error()` gives the
+ *     thread-local message.  No exceptions, no longjmp; re-entrant per stream.
+ *   - There is NO CPU fallback: without a CUDA device the compute calls fail with
+ *     SD_ERR_CUDA.
+ */
+#ifndef SPLICEDICE_B200_H
+#define SPLICEDICE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SD_ABI_VERSION 1
+
+#define SD_OK 0
+#define SD_ERR_INVALID 1      /* bad argument (null pointer, negative size, ld < n_samples ...) */
+#define SD_ERR_CUDA 2         /* CUDA runtime error; message carries cudaGetErrorString */
+#define SD_ERR_WORKSPACE 3    /* workspace too small */
+#define SD_ERR_OVERFLOW 4     /* adjacency does not fit int32 indices */
+#define SD_ERR_UNSUPPORTED 5
+
+/* ---- library ---------------------------------------------------------------- */
+int sd_version(void);                       /* SD_ABI_VERSION of the built library */
+const char *sd_last_error(void);            /* thread-local, never NULL */
+/* SM count / compute capability / memory of `device`. */
+int sd_device_info(int device, int *sm_count, int *cc_major, int *cc_minor, size_t *total_mem);
+
+/* ---- K1: overlap adjacency ("clusters") + output row order --------------------
+ * Replaces SPLICEDICE.getClusters (SPLICEDICE.py:230-255; twin
+ * counts_to_ps.determine_clusters, counts_to_ps.py:16-41) and the row index of
+ * SPLICEDICE.py:96.
+ *
+ * Input: J distinct junctions in any order as (chrom_rank, strand_rank, start, end);
+ * the ranks are dense ranks of the chromosome / strand STRINGS under python's str
+ * order (the host computes them: "chr10" < "chr2", "+" < "-").
+ *
+ * sd_cluster_build sorts by (chrom, strand, start, end) (:237), finds each junction's
+ * later-neighbour run and prior count (closed-interval overlap, :250), the overlap
+ * components (segmented running max of `end`), the output row of every junction
+ * (tuple order (chrom, start, end, strand), :96) and the CSR row pointer in output-row
+ * space.  It synchronises the stream to return nnz / n_components to the host.
+ * sd_cluster_fill then writes col_idx[nnz] (columns are output rows; each list ordered
+ * as the reference's: priors most-recent-first, then laters ascending, :247-254).  The
+ * build workspace must be passed, untouched, to sd_cluster_fill together with a second
+ * workspace sized by sd_cluster_fill_workspace_bytes(n_junctions, nnz).
+ * Preconditions: 0 <= start, end < 2^31; chrom_rank < 2^25; strand_rank < 2^8.
+ *
+ *   cluster_order[pos] = input index of the junction at position pos of cluster order
+ *   out_row[i]         = output row of input junction i
+ *   row_of_pos[pos]    = output row of the junction at cluster position pos
+ *   comp_id[pos]       = overlap-component id (non-decreasing in pos)
+ *   row_ptr[J+1]       = CSR pointer over output rows
+ * The *_workspace_bytes queries need a CUDA device (they return 0 and set sd_last_error()
+ * without one).
+ */
+size_t sd_cluster_workspace_bytes(int64_t n_junctions);
+size_t sd_cluster_fill_workspace_bytes(int64_t n_junctions, int64_t nnz);
+int sd_cluster_build(int64_t n_junctions,
+                     const int32_t *chrom_rank, const int32_t *strand_rank,
+                     const int32_t *start, const int32_t *end,
+                     int32_t *cluster_order, int32_t *out_row, int32_t *row_of_pos,
+                     int32_t *comp_id, int32_t *row_ptr,
+                     int64_t *nnz_host, int64_t *n_components_host,
+                     void *workspace, size_t workspace_bytes, void *stream);
+int sd_cluster_fill(int64_t n_junctions, int64_t nnz, const int32_t *row_of_pos,
+                    const int32_t *row_ptr, int32_t *col_idx,
+                    void *build_workspace, size_t build_workspace_bytes,
+                    void *fill_workspace, size_t fill_workspace_bytes, void *stream);
+
+/* ---- K2: exclusion aggregation fused with the PS divide -------------------------
+ * Replaces SPLICEDICE.calculatePsi (SPLICEDICE.py:297-310) and the arithmetic of
+ * counts_to_ps.writePsValues (counts_to_ps.py:62-68).
+ *
+ * For rows r in [row_begin, row_end):  exc[r,s] = sum_{c in adj(r)} counts[c,s]
+ * (exact integer sum; duplicates in the list count twice, as the reference's loop),
+ *   ps_f32[r,s] = (float)((double)inc / (double)(inc + exc))   -- calculatePsi's dtype chain
+ *   ps_f64[r,s] = (double)inc / (double)(inc + exc)            -- counts_to_ps
+ * 0/0 -> NaN; low_mask[r,s] != 0 -> ps_f32 = NaN (SPLICEDICE.py:307-309).
+ * Any of ps_f32 / ps_f64 / exc_out may be NULL (at least one must be set); counts must
+ * be non-negative.  `flags`: 0 = automatic kernel choice; see SD_QUANT_* below.
+ */
+#define SD_QUANT_AUTO 0u
+#define SD_QUANT_GATHER 1u        /* direct gather kernel (any alignment) */
+#define SD_QUANT_TILED 2u         /* TMA-staged shared-memory tile kernel (aligned inputs) */
+#define SD_QUANT_VARIANT_MASK 0xFFu
+/* bits 8..15: log2(rows per tile) override, bits 16..23: columns per slab / 32 override */
+int sd_quant_ps(int64_t n_junctions, int32_t n_samples,
+                const int32_t *counts, int64_t ld_counts,
+                const int32_t *row_ptr, const int32_t *col_idx,
+                const uint8_t *low_mask, int64_t ld_mask,
+                float *ps_f32, int64_t ld_ps32,
+                double *ps_f64, int64_t ld_ps64,
+                int64_t *exc_out, int64_t ld_exc,
+                int64_t row_begin, int64_t row_end,
+                uint32_t flags, void *stream);
+
+/* Host-buffer form of the PS path (the call a ctypes user makes): counts / ps are HOST
+ * pointers (pinned memory gives full PCIe rate), row_ptr / col_idx are HOST pointers.
+ * Transfers and the kernel are pipelined over row blocks on internal streams; the call
+ * returns when ps_f32 is complete.  `device` is the CUDA device ordinal. */
+int sd_quant_ps_host(int device, int64_t n_junctions, int32_t n_samples,
+                     const int32_t *counts, int64_t ld_counts,
+                     const int32_t *row_ptr, const int32_t *col_idx,
+                     const uint8_t *low_mask, int64_t ld_mask,
+                     float *ps_f32, int64_t ld_ps32);
+
+/* ---- K3: pairwise two-sided Fisher exact test ------------------------------------
+ * Replaces the hot loop of pairwise_fisher.run_with (pairwise_fisher.py:154-180) and
+ * scipy.stats.fisher_exact's two-sided branch (scipy 1.18.1, stats/_stats_py.py:5042-5108).
+ * For rows j in [row_begin, row_end) and pairs k < n_pairs:
+ *   p_out[j, k] = two-sided p of [[inc[j,a_k], inc[j,b_k]], [exc[j,a_k], exc[j,b_k]]]
+ * Tables with a zero margin give 1.0.  Entries must be non-negative (SD_ERR_INVALID otherwise,
+ * as scipy raises ValueError).  The calls synchronise the stream once (a max-reduction over the
+ * inputs sizes the log-factorial table, which is built on the host in binary128 the first time
+ * a size is needed and cached per device for the life of the process -- the library's only
+ * process-wide state, read-only once built).
+ */
+int sd_fisher_pairwise(int64_t n_junctions, int32_t n_samples,
+                       const int32_t *inc, int64_t ld_inc,
+                       const int64_t *exc, int64_t ld_exc,
+                       int64_t n_pairs, const int32_t *pair_a, const int32_t *pair_b,
+                       double *p_out, int64_t ld_p,
+                       int64_t row_begin, int64_t row_end, void *stream);
+/* Host-buffer form (the call a ctypes user makes): every pointer is a HOST pointer; row blocks
+ * of p-values are computed on one stream while the previous block is copied back on another.
+ * Returns when p_out is complete. */
+int sd_fisher_pairwise_host(int device, int64_t n_junctions, int32_t n_samples,
+                            const int32_t *inc, int64_t ld_inc,
+                            const int64_t *exc, int64_t ld_exc,
+                            int64_t n_pairs, const int32_t *pair_a, const int32_t *pair_b,
+                            double *p_out, int64_t ld_p);
+/* Element-wise form: p[i] for tables (a[i], b[i], c[i], d[i]) = [[a, b], [c, d]]. */
+int sd_fisher_tables(int64_t n_tables, const int64_t *a, const int64_t *b,
+                     const int64_t *c, const int64_t *d, double *p_out, void *stream);
+
+/* ---- K4: intron-retention ratio ----------------------------------------------------
+ * Replaces the arithmetic of ir_table.calculateIR (ir_table.py:118-132):
+ *   ir[r,s] = median[r,s] / (median[r,s] + inc[r,s] + sum_{c in adj(r)} inc[c,s]),  x/0 -> NaN
+ * (row_ptr == NULL: single-junction form, -s).  sd_rsd5: rsd[i] = std(cov[i,0:5]) / mean(cov[i,0:5])
+ * with numpy's population std.
+ */
+int sd_ir_ratio(int64_t n_junctions, int32_t n_samples,
+                const double *median, int64_t ld_median,
+                const int32_t *counts, int64_t ld_counts,
+                const int32_t *row_ptr, const int32_t *col_idx,
+                double *ir_out, int64_t ld_ir,
+                int64_t row_begin, int64_t row_end, void *stream);
+int sd_rsd5(int64_t n, const double *cov5, double *rsd_out, void *stream);
+
+/* ---- synthetic inputs + probes (bench / tests) --------------------------------------
+ * sd_synth_counts: the counter-based generator of splicedice_b200/synth.py:counts_host,
+ * bit for bit.  out[r - row0, c] for r in [row0, row0 + n_rows), c < n_cols.
+ * sd_probe_fp64: sustained FP64 FMA rate (GFLOP/s) of the device behind `stream`.
+ * sd_probe_copy: device-to-device copy bandwidth (GB/s, read + write bytes).
+ */
+int sd_synth_counts(uint64_t seed, int64_t row0, int64_t n_rows, int32_t n_cols,
+                    int64_t logical_cols, uint32_t scale,
+                    int32_t *out, int64_t ld_out, void *stream);
+int sd_probe_fp64(double *gflops_out, void *stream);
+int sd_probe_copy(int64_t bytes, double *gbs_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPLICEDICE_B200_H */

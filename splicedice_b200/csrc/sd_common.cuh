@@ -1,0 +1,123 @@
+// sd_common.cuh -- shared helpers for the splicedice_b200 CUDA library (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+
+#include "../../include/splicedice_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "splicedice_b200 targets sm_100a (B200) only"
+#endif
+
+namespace sd {
+
+// thread-local error text behind sd_last_error()
+std::string &last_error();
+int fail(int code, const char *fmt, ...);
+
+#define SD_CHECK_CUDA(expr)                                                               \
+    do {                                                                                  \
+        cudaError_t _e = (expr);                                                          \
+        if (_e != cudaSuccess)                                                            \
+            return ::sd::fail(SD_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                              __FILE__, __LINE__);                                        \
+    } while (0)
+
+#define SD_REQUIRE(cond, ...)                                   \
+    do {                                                        \
+        if (!(cond)) return ::sd::fail(SD_ERR_INVALID, __VA_ARGS__); \
+    } while (0)
+
+inline int check_launch(const char *what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(SD_ERR_CUDA, "%s launch: %s", what, cudaGetErrorString(e));
+    return SD_OK;
+}
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+constexpr int kSMs = 148;   // B200
+
+// ---- device helpers -----------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// mbarrier + 1-D bulk (TMA) copies, global -> shared::cta
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// bytes: multiple of 16; both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes,
+                                         uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+__device__ __forceinline__ int4 ldg_nc_v4(const int32_t *p)
+{
+    int4 v;
+    asm volatile("ld.global.nc.v4.s32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void stg_cs_v4(float *p, float a, float b, float c, float d)
+{
+    asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d)
+                 : "memory");
+}
+__device__ __forceinline__ void stg_cs_v2(double *p, double a, double b)
+{
+    asm volatile("st.global.cs.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+}
+__device__ __forceinline__ void stg_cs_v2(long long *p, long long a, long long b)
+{
+    asm volatile("st.global.cs.v2.s64 [%0], {%1,%2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+
+#endif  // __CUDACC__
+
+}  // namespace sd

@@ -1,0 +1,381 @@
+// sd_fisher.cu -- K3: two-sided Fisher exact test for every (junction, sample pair).
+//
+// Replaces the hot loop of pairwise_fisher.run_with
+// (/root/reference/splicedice/pairwise_fisher.py:154-180) and scipy.stats.fisher_exact's
+// two-sided branch; the per-table arithmetic is in sd_fisher_math.cuh.
+//
+// Mapping: one warp per (junction, 32-pair tile), one table per lane; persistent CTAs stride
+// over the tiles.  The double-double log-factorial table is staged once per CTA in shared
+// memory (entries beyond the staged prefix come from the global copy through L1/L2).  The
+// junction's inclusion / exclusion row is a few hundred bytes and is gathered through L1; the
+// 32 p-values of a tile leave as one 256-byte coalesced store.  The kernel is FP64-pipe bound:
+// ~9 FP64 instructions per summed tail term, no division or exp in the loop.
+#include <algorithm>
+#include <mutex>
+#include <vector>
+
+#include "sd_common.cuh"
+#include "sd_fisher_math.cuh"
+#include "sd_lgtable.h"
+
+namespace sd {
+
+struct DeviceTable {
+    const double2 *smem;     // staged prefix
+    const double2 *gmem;     // full table
+    int64_t n_smem, n_gmem;
+    __device__ __forceinline__ double2 load(int64_t k) const
+    {
+        if (k < n_smem) return smem[k];
+        if (k < n_gmem) return __ldg(gmem + k);
+        return make_double2(lgamma((double)k + 1.0), 0.0);
+    }
+    __device__ __forceinline__ double hi(int64_t k) const { return load(k).x; }
+    __device__ __forceinline__ fisher::dd get(int64_t k) const
+    {
+        double2 v = load(k);
+        return fisher::dd_make(v.x, v.y);
+    }
+};
+
+constexpr int kFisherThreads = 256;
+
+struct FisherParams {
+    int64_t n_junctions;
+    int32_t n_samples;
+    const int32_t *inc;
+    int64_t ld_inc;
+    const int64_t *exc;
+    int64_t ld_exc;
+    int64_t n_pairs;
+    const int32_t *pair_a, *pair_b;
+    double *p_out;
+    int64_t ld_p;
+    int64_t row_begin, row_end;
+    const double2 *table;
+    int64_t table_entries;
+    int32_t smem_entries;
+};
+
+__device__ __forceinline__ void stage_table(double2 *s_tab, const double2 *g_tab, int n)
+{
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s_tab[i] = __ldg(g_tab + i);
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kFisherThreads, 2) fisher_pairwise_kernel(const FisherParams p)
+{
+    extern __shared__ __align__(16) double2 s_tab[];
+    stage_table(s_tab, p.table, p.smem_entries);
+    const DeviceTable tab{s_tab, p.table, p.smem_entries, p.table_entries};
+
+    const int lane = threadIdx.x & 31;
+    const int64_t tiles_per_row = (p.n_pairs + 31) / 32;
+    const int64_t n_items = (p.row_end - p.row_begin) * tiles_per_row;
+    const int64_t warp0 = (int64_t)blockIdx.x * (kFisherThreads / 32) + (threadIdx.x >> 5);
+    const int64_t n_warps = (int64_t)gridDim.x * (kFisherThreads / 32);
+    for (int64_t item = warp0; item < n_items; item += n_warps) {
+        const int64_t j = p.row_begin + item / tiles_per_row;
+        const int64_t k = (item % tiles_per_row) * 32 + lane;
+        if (k >= p.n_pairs) continue;
+        const int sa = __ldg(p.pair_a + k), sb = __ldg(p.pair_b + k);
+        const int64_t a = __ldg(p.inc + j * p.ld_inc + sa), b = __ldg(p.inc + j * p.ld_inc + sb);
+        const int64_t c = __ldg(p.exc + j * p.ld_exc + sa), d = __ldg(p.exc + j * p.ld_exc + sb);
+        const double pv = fisher::two_sided(tab, a, b, c, d);
+        __stcs(p.p_out + j * p.ld_p + k, pv);
+    }
+}
+
+__global__ void __launch_bounds__(kFisherThreads, 2) fisher_tables_kernel(
+    int64_t n, const int64_t *__restrict__ a, const int64_t *__restrict__ b,
+    const int64_t *__restrict__ c, const int64_t *__restrict__ d, double *__restrict__ out,
+    const double2 *table, int64_t table_entries, int32_t smem_entries)
+{
+    extern __shared__ __align__(16) double2 s_tab[];
+    stage_table(s_tab, table, smem_entries);
+    const DeviceTable tab{s_tab, table, smem_entries, table_entries};
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = fisher::two_sided(tab, a[i], b[i], c[i], d[i]);
+}
+
+// max over the row range of inc + exc (pairwise) or of a + b + c + d (tables); also flags
+// negative entries (scipy raises ValueError on them, stats/_stats_py.py:5048-5049)
+__global__ void __launch_bounds__(256) fisher_scan_pairwise(const FisherParams p, unsigned long long *max_out,
+                                                            int *neg_out)
+{
+    const int64_t cells = (p.row_end - p.row_begin) * p.n_samples;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    unsigned long long m = 0;
+    int neg = 0;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < cells; g += stride) {
+        const int64_t j = p.row_begin + g / p.n_samples;
+        const int s = (int)(g % p.n_samples);
+        const int64_t a = p.inc[j * p.ld_inc + s], c = p.exc[j * p.ld_exc + s];
+        if (a < 0 || c < 0) neg = 1;
+        else m = max(m, (unsigned long long)(a + c));
+    }
+    for (int o = 16; o; o >>= 1) {
+        m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+        neg |= __shfl_xor_sync(0xffffffffu, neg, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (m) atomicMax(max_out, m);
+        if (neg) atomicOr(neg_out, 1);
+    }
+}
+
+__global__ void __launch_bounds__(256) fisher_scan_tables(int64_t n, const int64_t *a, const int64_t *b,
+                                                          const int64_t *c, const int64_t *d,
+                                                          unsigned long long *max_out, int *neg_out)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    unsigned long long m = 0;
+    int neg = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        if (a[i] < 0 || b[i] < 0 || c[i] < 0 || d[i] < 0) neg = 1;
+        else m = max(m, (unsigned long long)(a[i] + b[i] + c[i] + d[i]));
+    }
+    for (int o = 16; o; o >>= 1) {
+        m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+        neg |= __shfl_xor_sync(0xffffffffu, neg, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (m) atomicMax(max_out, m);
+        if (neg) atomicOr(neg_out, 1);
+    }
+}
+
+// ---- device copies of the table: one per device, grown on demand, never shrunk ----------
+namespace {
+constexpr int64_t kTableCap = int64_t(1) << 22;      // 4 Mi entries = 64 MB; beyond: lgamma()
+constexpr int kMaxDevices = 64;
+std::mutex g_tab_mu;
+double2 *g_tab_dev[kMaxDevices] = {};
+int64_t g_tab_entries[kMaxDevices] = {};
+}  // namespace
+
+// Returns a device table with at least min(need, kTableCap) entries for the current device.
+// Grows by reallocation; the old block is left allocated (kernels in flight may still read it)
+// -- at most log2(cap) of them over the life of the process.
+static int device_table(int64_t need, const double2 **table, int64_t *entries, cudaStream_t stream)
+{
+    int dev = 0;
+    SD_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev >= kMaxDevices) return fail(SD_ERR_UNSUPPORTED, "device ordinal %d too large", dev);
+    need = std::min(std::max<int64_t>(need, 4096), kTableCap);
+    std::lock_guard<std::mutex> lock(g_tab_mu);
+    if (g_tab_entries[dev] < need) {
+        int64_t n = 4096;
+        while (n < need) n <<= 1;
+        std::vector<double> host;
+        lgtable_host(n, &host);
+        double2 *d = nullptr;
+        SD_CHECK_CUDA(cudaMalloc(&d, (size_t)n * sizeof(double2)));
+        SD_CHECK_CUDA(cudaMemcpyAsync(d, host.data(), (size_t)n * sizeof(double2), cudaMemcpyHostToDevice, stream));
+        SD_CHECK_CUDA(cudaStreamSynchronize(stream));    // `host` dies at scope exit
+        g_tab_dev[dev] = d;
+        g_tab_entries[dev] = n;
+    }
+    *table = g_tab_dev[dev];
+    *entries = g_tab_entries[dev];
+    return SD_OK;
+}
+
+constexpr int kSmemEntriesMax = 6144;      // 96 KB of double2: two CTAs per SM
+
+static int scan_result(unsigned long long *d_max, int *d_neg, cudaStream_t stream, int64_t *max_total,
+                       const char *who)
+{
+    unsigned long long h_max = 0;
+    int h_neg = 0;
+    SD_CHECK_CUDA(cudaMemcpyAsync(&h_max, d_max, sizeof h_max, cudaMemcpyDeviceToHost, stream));
+    SD_CHECK_CUDA(cudaMemcpyAsync(&h_neg, d_neg, sizeof h_neg, cudaMemcpyDeviceToHost, stream));
+    SD_CHECK_CUDA(cudaStreamSynchronize(stream));
+    if (h_neg) return fail(SD_ERR_INVALID, "%s: all table entries must be non-negative", who);
+    *max_total = (int64_t)h_max;
+    return SD_OK;
+}
+
+static int fisher_grid(const void *kernel, size_t smem)
+{
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kFisherThreads, smem) != cudaSuccess ||
+        per_sm < 1)
+        per_sm = 1;
+    int dev = 0, sms = kSMs;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms * per_sm;
+}
+
+int launch_fisher_pairwise(FisherParams p, cudaStream_t stream)
+{
+    // table size: the largest table total in the row range is at most 2 * max(inc + exc)
+    unsigned long long *d_max = nullptr;
+    SD_CHECK_CUDA(cudaMallocAsync(&d_max, 16, stream));
+    SD_CHECK_CUDA(cudaMemsetAsync(d_max, 0, 16, stream));
+    int *d_neg = reinterpret_cast<int *>(d_max + 1);
+    const int64_t cells = (p.row_end - p.row_begin) * p.n_samples;
+    fisher_scan_pairwise<<<(int)std::min<int64_t>((cells + 255) / 256, kSMs * 8), 256, 0, stream>>>(p, d_max, d_neg);
+    int64_t max_cell = 0;
+    int rc = scan_result(d_max, d_neg, stream, &max_cell, "sd_fisher_pairwise");
+    cudaFreeAsync(d_max, stream);
+    if (rc != SD_OK) return rc;
+    if ((rc = device_table(2 * max_cell + 2, &p.table, &p.table_entries, stream)) != SD_OK) return rc;
+    p.smem_entries = (int32_t)std::min<int64_t>(std::min<int64_t>(2 * max_cell + 2, p.table_entries), kSmemEntriesMax);
+    const size_t smem = (size_t)p.smem_entries * sizeof(double2);
+    SD_CHECK_CUDA(cudaFuncSetAttribute(fisher_pairwise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(kSmemEntriesMax * sizeof(double2))));
+    const int64_t items = (p.row_end - p.row_begin) * ((p.n_pairs + 31) / 32);
+    int grid = fisher_grid((const void *)fisher_pairwise_kernel, smem);
+    grid = (int)std::min<int64_t>(grid, (items + kFisherThreads / 32 - 1) / (kFisherThreads / 32));
+    fisher_pairwise_kernel<<<grid, kFisherThreads, smem, stream>>>(p);
+    return check_launch("fisher_pairwise_kernel");
+}
+
+}  // namespace sd
+
+extern "C" {
+
+int sd_fisher_pairwise(int64_t n_junctions, int32_t n_samples, const int32_t *inc, int64_t ld_inc,
+                       const int64_t *exc, int64_t ld_exc, int64_t n_pairs, const int32_t *pair_a,
+                       const int32_t *pair_b, double *p_out, int64_t ld_p, int64_t row_begin,
+                       int64_t row_end, void *stream)
+{
+    SD_REQUIRE(n_junctions >= 0 && n_samples >= 0 && n_pairs >= 0, "sd_fisher_pairwise: negative size");
+    SD_REQUIRE(row_begin >= 0 && row_begin <= row_end && row_end <= n_junctions,
+               "sd_fisher_pairwise: row range outside [0, n_junctions)");
+    if (row_begin == row_end || n_pairs == 0) return SD_OK;
+    SD_REQUIRE(inc && exc && pair_a && pair_b && p_out, "sd_fisher_pairwise: null pointer");
+    SD_REQUIRE(ld_inc >= n_samples && ld_exc >= n_samples && ld_p >= n_pairs, "sd_fisher_pairwise: ld too small");
+    sd::FisherParams p{};
+    p.n_junctions = n_junctions; p.n_samples = n_samples;
+    p.inc = inc; p.ld_inc = ld_inc; p.exc = exc; p.ld_exc = ld_exc;
+    p.n_pairs = n_pairs; p.pair_a = pair_a; p.pair_b = pair_b;
+    p.p_out = p_out; p.ld_p = ld_p; p.row_begin = row_begin; p.row_end = row_end;
+    return sd::launch_fisher_pairwise(p, (cudaStream_t)stream);
+}
+
+int sd_fisher_tables(int64_t n_tables, const int64_t *a, const int64_t *b, const int64_t *c,
+                     const int64_t *d, double *p_out, void *stream_)
+{
+    SD_REQUIRE(n_tables >= 0, "sd_fisher_tables: negative size");
+    if (n_tables == 0) return SD_OK;
+    SD_REQUIRE(a && b && c && d && p_out, "sd_fisher_tables: null pointer");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    unsigned long long *d_max = nullptr;
+    SD_CHECK_CUDA(cudaMallocAsync(&d_max, 16, stream));
+    SD_CHECK_CUDA(cudaMemsetAsync(d_max, 0, 16, stream));
+    int *d_neg = reinterpret_cast<int *>(d_max + 1);
+    sd::fisher_scan_tables<<<(int)std::min<int64_t>((n_tables + 255) / 256, sd::kSMs * 8), 256, 0, stream>>>(
+        n_tables, a, b, c, d, d_max, d_neg);
+    int64_t max_total = 0;
+    int rc = sd::scan_result(d_max, d_neg, stream, &max_total, "sd_fisher_tables");
+    cudaFreeAsync(d_max, stream);
+    if (rc != SD_OK) return rc;
+    const double2 *table = nullptr;
+    int64_t entries = 0;
+    if ((rc = sd::device_table(max_total + 1, &table, &entries, stream)) != SD_OK) return rc;
+    const int32_t smem_entries =
+        (int32_t)std::min<int64_t>(std::min<int64_t>(max_total + 1, entries), sd::kSmemEntriesMax);
+    const size_t smem = (size_t)smem_entries * sizeof(double2);
+    SD_CHECK_CUDA(cudaFuncSetAttribute(sd::fisher_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(sd::kSmemEntriesMax * sizeof(double2))));
+    int grid = sd::fisher_grid((const void *)sd::fisher_tables_kernel, smem);
+    grid = (int)std::min<int64_t>(grid, (n_tables + sd::kFisherThreads - 1) / sd::kFisherThreads);
+    sd::fisher_tables_kernel<<<grid, sd::kFisherThreads, smem, stream>>>(n_tables, a, b, c, d, p_out, table,
+                                                                        entries, smem_entries);
+    return sd::check_launch("fisher_tables_kernel");
+}
+
+// Host-buffer form: inc / exc / pairs / p_out are HOST pointers.  Row blocks of p-values are
+// computed on one stream and copied back on another, so the 8 B/test of D2H traffic overlaps
+// the FP64 work.
+int sd_fisher_pairwise_host(int device, int64_t n_junctions, int32_t n_samples, const int32_t *inc,
+                            int64_t ld_inc, const int64_t *exc, int64_t ld_exc, int64_t n_pairs,
+                            const int32_t *pair_a, const int32_t *pair_b, double *p_out, int64_t ld_p)
+{
+    SD_REQUIRE(n_junctions >= 0 && n_samples >= 0 && n_pairs >= 0, "sd_fisher_pairwise_host: negative size");
+    if (n_junctions == 0 || n_pairs == 0) return SD_OK;
+    SD_REQUIRE(inc && exc && pair_a && pair_b && p_out, "sd_fisher_pairwise_host: null pointer");
+    SD_REQUIRE(ld_inc >= n_samples && ld_exc >= n_samples && ld_p >= n_pairs,
+               "sd_fisher_pairwise_host: ld too small");
+    for (int64_t k = 0; k < n_pairs; ++k)
+        SD_REQUIRE(pair_a[k] >= 0 && pair_a[k] < n_samples && pair_b[k] >= 0 && pair_b[k] < n_samples,
+                   "sd_fisher_pairwise_host: pair %lld out of range", (long long)k);
+    const int64_t J = n_junctions;
+    int prev_dev = 0;
+    SD_CHECK_CUDA(cudaGetDevice(&prev_dev));
+    SD_CHECK_CUDA(cudaSetDevice(device));
+    cudaStream_t s_k = nullptr, s_out = nullptr;
+    int32_t *d_inc = nullptr, *d_pa = nullptr, *d_pb = nullptr;
+    int64_t *d_exc = nullptr;
+    double *d_p = nullptr;
+    std::vector<cudaEvent_t> ev;
+    int rc = SD_OK;
+    auto cleanup = [&]() {
+        for (auto e : ev) cudaEventDestroy(e);
+        if (s_out) cudaStreamSynchronize(s_out);
+        if (s_k) cudaStreamSynchronize(s_k);
+        cudaFree(d_inc); cudaFree(d_exc); cudaFree(d_pa); cudaFree(d_pb); cudaFree(d_p);
+        if (s_k) cudaStreamDestroy(s_k);
+        if (s_out) cudaStreamDestroy(s_out);
+        cudaSetDevice(prev_dev);
+    };
+#define SD_TRY(expr)                                                                              \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            rc = sd::fail(SD_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                          __LINE__);                                                              \
+            cleanup();                                                                            \
+            return rc;                                                                            \
+        }                                                                                         \
+    } while (0)
+    SD_TRY(cudaStreamCreateWithFlags(&s_k, cudaStreamNonBlocking));
+    SD_TRY(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+    // p-value blocks of ~64 MB, double buffered
+    int64_t block_rows = std::max<int64_t>(1, (int64_t)(64u << 20) / (n_pairs * 8));
+    block_rows = std::min(block_rows, J);
+    SD_TRY(cudaMalloc(&d_inc, (size_t)J * n_samples * 4));
+    SD_TRY(cudaMalloc(&d_exc, (size_t)J * n_samples * 8));
+    SD_TRY(cudaMalloc(&d_pa, (size_t)n_pairs * 4));
+    SD_TRY(cudaMalloc(&d_pb, (size_t)n_pairs * 4));
+    SD_TRY(cudaMalloc(&d_p, (size_t)2 * block_rows * n_pairs * 8));
+    SD_TRY(cudaMemcpy2DAsync(d_inc, (size_t)n_samples * 4, inc, (size_t)ld_inc * 4, (size_t)n_samples * 4, (size_t)J,
+                             cudaMemcpyHostToDevice, s_k));
+    SD_TRY(cudaMemcpy2DAsync(d_exc, (size_t)n_samples * 8, exc, (size_t)ld_exc * 8, (size_t)n_samples * 8, (size_t)J,
+                             cudaMemcpyHostToDevice, s_k));
+    SD_TRY(cudaMemcpyAsync(d_pa, pair_a, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, s_k));
+    SD_TRY(cudaMemcpyAsync(d_pb, pair_b, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, s_k));
+    const int64_t n_blocks = (J + block_rows - 1) / block_rows;
+    ev.resize((size_t)2 * n_blocks, nullptr);
+    for (auto &e : ev) SD_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (int64_t b = 0; b < n_blocks; ++b) {
+        const int64_t r0 = b * block_rows, r1 = std::min(J, r0 + block_rows);
+        double *buf = d_p + (b & 1) * block_rows * n_pairs;
+        if (b >= 2) SD_TRY(cudaStreamWaitEvent(s_k, ev[2 * (b - 2) + 1], 0));   // buffer drained
+        sd::FisherParams p{};
+        p.n_junctions = J; p.n_samples = n_samples;
+        p.inc = d_inc; p.ld_inc = n_samples; p.exc = d_exc; p.ld_exc = n_samples;
+        p.n_pairs = n_pairs; p.pair_a = d_pa; p.pair_b = d_pb;
+        p.p_out = buf - r0 * n_pairs; p.ld_p = n_pairs; p.row_begin = r0; p.row_end = r1;
+        rc = sd::launch_fisher_pairwise(p, s_k);
+        if (rc != SD_OK) { cleanup(); return rc; }
+        SD_TRY(cudaEventRecord(ev[2 * b], s_k));
+        SD_TRY(cudaStreamWaitEvent(s_out, ev[2 * b], 0));
+        if (ld_p == n_pairs)
+            SD_TRY(cudaMemcpyAsync(p_out + r0 * ld_p, buf, (size_t)(r1 - r0) * n_pairs * 8, cudaMemcpyDeviceToHost, s_out));
+        else
+            SD_TRY(cudaMemcpy2DAsync(p_out + r0 * ld_p, (size_t)ld_p * 8, buf, (size_t)n_pairs * 8, (size_t)n_pairs * 8,
+                                     (size_t)(r1 - r0), cudaMemcpyDeviceToHost, s_out));
+        SD_TRY(cudaEventRecord(ev[2 * b + 1], s_out));
+    }
+    SD_TRY(cudaStreamSynchronize(s_out));
+#undef SD_TRY
+    cleanup();
+    return SD_OK;
+}
+
+}  // extern "C"

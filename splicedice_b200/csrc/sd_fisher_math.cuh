@@ -1,0 +1,249 @@
+// sd_fisher_math.cuh -- per-table arithmetic of the two-sided Fisher exact test.
+//
+// Follows the control flow of scipy.stats.fisher_exact (scipy 1.18.1,
+// stats/_stats_py.py:5042-5108; the call the reference makes at
+// /root/reference/splicedice/pairwise_fisher.py:165,179):
+//   - any zero margin                         -> p = 1                         (:5055-5058)
+//   - mode = int((n+1)(n1+1)/(n1+n2+2))       (float divide, truncation)       (:5078)
+//   - |pexact - pmode| / max <= 1e-14         -> p = 1                         (:5085-5086)
+//   - observed below the mode: p = cdf(a) + sum of the upper-side x with pmf(x) < pexact*(1+1e-14)
+//     observed above the mode: p = sf(a-1) + sum of the lower-side x with pmf(x) <= pexact*(1+1e-14)
+//                                                                              (:5088-5101)
+//   - p = min(p, 1)                                                            (:5106)
+// The pmf itself is never evaluated per support point.  With t(x) = pmf(x)/pmf(a):
+//   p = pmf(a) * ( S(a, away from the mode) + t(g) * S(g, away from the mode) )
+// where g is the first far-side point that scipy's search admits and S(x0, dir) =
+// 1 + r1 + r1 r2 + ... is the tail sum relative to its first term, accumulated with the exact
+// rational term ratio  pmf(x+1)/pmf(x) = (n1-x)(n-x) / ((x+1)(n2-n+x+1))  as a
+// numerator/denominator pair (no division in the loop) and cut when a term drops below
+// 2^-56 of the running sum.  pmf(a), t(g) and every "is pmf(x) within the tie window of
+// pmf(a)" decision come from a double-double log-factorial table (sd_lgtable.cpp).
+//
+// The header compiles for the device (sd_fisher.cu) and, without nvcc, for the host: the host
+// build exists only so tests/ can check this arithmetic against scipy golden vectors on
+// machines with no GPU.  Nothing in the product calls the host build.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define SD_HD __host__ __device__ __forceinline__
+#else
+#define SD_HD inline
+#endif
+
+namespace sd {
+namespace fisher {
+
+struct dd {
+    double hi, lo;
+};
+
+SD_HD dd dd_make(double hi, double lo) { dd r; r.hi = hi; r.lo = lo; return r; }
+
+SD_HD dd dd_add(dd x, dd y)
+{
+    double s = x.hi + y.hi;
+    double bb = s - x.hi;
+    double e = (x.hi - (s - bb)) + (y.hi - bb);
+    e += x.lo + y.lo;
+    double hi = s + e;
+    return dd_make(hi, e - (hi - s));
+}
+SD_HD dd dd_sub(dd x, dd y) { return dd_add(x, dd_make(-y.hi, -y.lo)); }
+
+constexpr double kEps = 1e-14;                          // scipy's epsilon (:5082)
+constexpr double kLogGamma = 9.992007221626358e-15;     // log(1 + 1e-14) with 1 + 1e-14 formed in binary64
+constexpr double kTieWindow = 1.0000000000000051e-14;   // -log(1 - 1e-14)
+constexpr double kCut = 1.3877787807814457e-17;         // 2^-56: tail truncation relative to the sum
+constexpr double kBig = 3.273390607896142e150;          // 2^500
+constexpr double kSmall = 3.054936363499605e-151;       // 2^-500
+
+// Tail sum relative to its first term.  (p, q) are the two table cells that shrink along the
+// walk, (u, v) the two that grow:  term_k / term_{k-1} = (p-k+1)(q-k+1) / ((u+k)(v+k)).
+SD_HD double tail_sum(double p, double q, double u, double v)
+{
+    double steps = p < q ? p : q;                  // the ratio is zero after min(p, q) steps
+    double num_p = p, num_q = q, den_u = u + 1.0, den_v = v + 1.0;
+    double P = 1.0, Q = 1.0, A = 1.0;             // term = P / Q, sum = A / Q
+    while (steps > 0.0) {
+        int burst = steps < 4.0 ? (int)steps : 4;
+        for (int i = 0; i < burst; ++i) {
+            P *= num_p * num_q;
+            double den = den_u * den_v;
+            Q *= den;
+            A = fma(A, den, P);
+            num_p -= 1.0; num_q -= 1.0; den_u += 1.0; den_v += 1.0;
+        }
+        steps -= (double)burst;
+        if (P < kCut * A) break;
+        if (Q > kBig) { P *= kSmall; Q *= kSmall; A *= kSmall; }
+    }
+    return A / Q;
+}
+
+// G(x) = lg[x] + lg[n1-x] + lg[n-x] + lg[n2-n+x]; log pmf(x) = const - G(x).
+template <class Table>
+struct Problem {
+    const Table &tab;
+    int64_t n1, n2, n, N;
+    int64_t a, b, c, d;
+    double tol;   // bound on the error of a hi-only evaluation of G(a) - G(x)
+
+    // f(x) = log(pmf(x) / pmf(a)) from the hi words only
+    SD_HD double f_fast(int64_t x) const
+    {
+        return (tab.hi(a) - tab.hi(x)) + (tab.hi(b) - tab.hi(n1 - x)) + (tab.hi(c) - tab.hi(n - x)) +
+               (tab.hi(d) - tab.hi(n2 - n + x));
+    }
+    SD_HD dd f_exact(int64_t x) const
+    {
+        dd s = dd_sub(tab.get(a), tab.get(x));
+        s = dd_add(s, dd_sub(tab.get(b), tab.get(n1 - x)));
+        s = dd_add(s, dd_sub(tab.get(c), tab.get(n - x)));
+        s = dd_add(s, dd_sub(tab.get(d), tab.get(n2 - n + x)));
+        return s;
+    }
+    // scipy's far-side admission test: pmf(x) <= pexact * (1 + 1e-14)
+    SD_HD bool admitted(int64_t x) const
+    {
+        double f = f_fast(x);
+        if (fabs(f - kLogGamma) > tol) return f < kLogGamma;
+        dd fe = f_exact(x);
+        return fe.hi + fe.lo <= kLogGamma;
+    }
+};
+
+template <class Table>
+SD_HD double two_sided(const Table &tab, int64_t a, int64_t b, int64_t c, int64_t d)
+{
+    const int64_t n1 = a + b, n2 = c + d, n = a + c, N = n1 + n2;
+    if (n1 == 0 || n2 == 0 || n == 0 || b + d == 0) return 1.0;
+    const int64_t lo = n - n2 > 0 ? n - n2 : 0;
+    const int64_t hi = n1 < n ? n1 : n;
+    // numpy: int64 product, float64 divide, int() truncation
+    const int64_t mode = (int64_t)((double)((n + 1) * (n1 + 1)) / (double)(N + 2));
+    if (a == mode) return 1.0;
+
+    Problem<Table> pr{tab, n1, n2, n, N, a, b, c, d, 0.0};
+    pr.tol = 64.0 * 2.220446049250313e-16 * (tab.hi(N) + 1.0);
+
+    // tie between the observed table and the mode (plateau or mirror twin)
+    {
+        double fm = pr.f_fast(mode);
+        if (fabs(fm) <= pr.tol + kTieWindow) {
+            dd fe = pr.f_exact(mode);
+            if (fabs(fe.hi + fe.lo) <= kTieWindow) return 1.0;
+        }
+    }
+
+    // log pmf(a) in double-double
+    dd lp = dd_add(tab.get(n1), tab.get(n2));
+    lp = dd_add(lp, tab.get(n));
+    lp = dd_add(lp, tab.get(N - n));
+    lp = dd_sub(lp, tab.get(N));
+    lp = dd_sub(lp, tab.get(a));
+    lp = dd_sub(lp, tab.get(b));
+    lp = dd_sub(lp, tab.get(c));
+    lp = dd_sub(lp, tab.get(d));
+    double pexact = exp(lp.hi);
+    pexact = fma(pexact, lp.lo, pexact);
+
+    double s_near, s_far = 0.0;
+    int64_t g;          // first admitted far-side point
+    bool have_far;
+    if (a < mode) {
+        s_near = tail_sum((double)a, (double)d, (double)b, (double)c);         // a, a-1, ... lo
+        // smallest g in (mode, hi] with admitted(g)
+        int64_t lo_x = mode, hi_x = hi + 1;
+        int64_t x = 2 * mode - a;
+        if (x > hi) x = hi;
+        if (x <= mode) x = mode + 1;
+        if (x <= hi) {
+            int64_t step = 1;
+            if (pr.admitted(x)) {
+                hi_x = x;
+                while (true) {
+                    int64_t y = hi_x - step;
+                    if (y <= lo_x) break;
+                    if (pr.admitted(y)) { hi_x = y; step *= 2; }
+                    else { lo_x = y; break; }
+                }
+            } else {
+                lo_x = x;
+                while (true) {
+                    int64_t y = lo_x + step;
+                    if (y >= hi_x) break;
+                    if (pr.admitted(y)) { hi_x = y; break; }
+                    lo_x = y; step *= 2;
+                }
+            }
+            while (hi_x - lo_x > 1) {
+                int64_t mid = lo_x + (hi_x - lo_x) / 2;
+                if (pr.admitted(mid)) hi_x = mid; else lo_x = mid;
+            }
+        }
+        g = hi_x;
+        have_far = g <= hi;
+        if (have_far)
+            s_far = tail_sum((double)(n1 - g), (double)(n - g), (double)g, (double)(n2 - n + g));
+    } else {
+        s_near = tail_sum((double)b, (double)c, (double)a, (double)d);         // a, a+1, ... hi
+        // largest g in [lo, mode) with admitted(g)
+        int64_t lo_x = lo - 1, hi_x = mode;
+        int64_t x = 2 * mode - a;
+        if (x < lo) x = lo;
+        if (x >= mode) x = mode - 1;
+        if (x >= lo) {
+            int64_t step = 1;
+            if (pr.admitted(x)) {
+                lo_x = x;
+                while (true) {
+                    int64_t y = lo_x + step;
+                    if (y >= hi_x) break;
+                    if (pr.admitted(y)) { lo_x = y; step *= 2; }
+                    else { hi_x = y; break; }
+                }
+            } else {
+                hi_x = x;
+                while (true) {
+                    int64_t y = hi_x - step;
+                    if (y <= lo_x) break;
+                    if (pr.admitted(y)) { lo_x = y; break; }
+                    hi_x = y; step *= 2;
+                }
+            }
+            while (hi_x - lo_x > 1) {
+                int64_t mid = lo_x + (hi_x - lo_x) / 2;
+                if (pr.admitted(mid)) lo_x = mid; else hi_x = mid;
+            }
+        }
+        g = lo_x;
+        have_far = g >= lo;
+        if (have_far)
+            s_far = tail_sum((double)g, (double)(n2 - n + g), (double)(n1 - g), (double)(n - g));
+    }
+    double rel = s_near;
+    if (have_far) {
+        dd fg = pr.f_exact(g);
+        double tg = exp(fg.hi);
+        tg = fma(tg, fg.lo, tg);
+        rel = fma(tg, s_far, s_near);
+    }
+    double p = pexact * rel;
+    return p > 1.0 ? 1.0 : p;
+}
+
+// hypergeometric support size of a table (0 for a zero-margin table): the work unit of the
+// FP64 model in DESIGN.md.
+SD_HD int64_t support_size(int64_t a, int64_t b, int64_t c, int64_t d)
+{
+    const int64_t n1 = a + b, n2 = c + d, n = a + c;
+    if (n1 == 0 || n2 == 0 || n == 0 || b + d == 0) return 0;
+    const int64_t lo = n - n2 > 0 ? n - n2 : 0, hi = n1 < n ? n1 : n;
+    return hi - lo + 1;
+}
+
+}  // namespace fisher
+}  // namespace sd

@@ -1,0 +1,40 @@
+// fisher_twin.cpp -- TEST-ONLY host build of splicedice_b200/csrc/sd_fisher_math.cuh.
+// Lets the CPU test-suite check the kernel's per-table arithmetic against the scipy golden
+// vectors without a GPU.  Not part of the product: nothing under splicedice_b200/ loads it.
+#include <quadmath.h>
+#include <stdint.h>
+
+#include <vector>
+
+#include "../../splicedice_b200/csrc/sd_fisher_math.cuh"
+#include "../../splicedice_b200/csrc/sd_lgtable.h"
+
+namespace {
+struct HostTable {
+    const double *t;
+    int64_t n;
+    double hi(int64_t k) const { return k < n ? t[2 * k] : lgamma((double)k + 1.0); }
+    sd::fisher::dd get(int64_t k) const
+    {
+        return k < n ? sd::fisher::dd_make(t[2 * k], t[2 * k + 1])
+                     : sd::fisher::dd_make(lgamma((double)k + 1.0), 0.0);
+    }
+};
+}  // namespace
+
+extern "C" int fisher_twin_batch(int64_t count, const int64_t *a, const int64_t *b, const int64_t *c,
+                                 const int64_t *d, double *out, int64_t table_cap)
+{
+    int64_t nmax = 0;
+    for (int64_t i = 0; i < count; ++i) {
+        int64_t N = a[i] + b[i] + c[i] + d[i];
+        if (N > nmax) nmax = N;
+    }
+    int64_t entries = nmax + 1;
+    if (table_cap > 0 && entries > table_cap) entries = table_cap;
+    std::vector<double> tab;
+    sd::lgtable_host(entries, &tab);
+    HostTable T{tab.data(), entries};
+    for (int64_t i = 0; i < count; ++i) out[i] = sd::fisher::two_sided(T, a[i], b[i], c[i], d[i]);
+    return 0;
+}

@@ -1,0 +1,105 @@
+"""K3 parity on the GPU: two-sided Fisher p-values vs scipy goldens and the binary128 oracle."""
+import numpy as np
+import pytest
+
+from oracle import fisher_c, oracle_np
+from tests import util
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+RTOL = 1e-9          # BASELINE.json north_star: 1e-9 relative for p > 1e-300
+
+
+def _ops():
+    from splicedice_b200 import native, ops
+    ops.require_cuda()
+    return native, ops
+
+
+def _check(got, want, rtol=RTOL):
+    ok = want > 1e-300
+    rel = np.abs(got[ok] - want[ok]) / want[ok]
+    assert rel.max(initial=0.0) <= rtol, f"max rel err {rel.max()}"
+    assert np.all(got[~ok] <= 1e-299)
+
+
+def test_scipy_golden_tables():
+    _, ops = _ops()
+    g = util.load_npz("fisher_tables.npz")
+    t, p = g["tables"], g["p"]
+    got = ops.fisher_tables(t[:, 0], t[:, 1], t[:, 2], t[:, 3]).cpu().numpy()
+    _check(got, p)
+    assert np.array_equal(got[p == 1.0], p[p == 1.0])      # ties / zero margins are exactly 1
+
+
+def test_exact_rational_small_tables():
+    _, ops = _ops()
+    g = util.load_npz("fisher_exact_small.npz")
+    t, p = g["tables"], g["p"]
+    got = ops.fisher_tables(t[:, 0], t[:, 1], t[:, 2], t[:, 3]).cpu().numpy()
+    np.testing.assert_allclose(got, p, rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("scale,n", [(4, 100000), (40, 200000), (400, 200000), (5000, 50000), (200000, 3000)])
+def test_random_tables_vs_binary128_oracle(scale, n):
+    _, ops = _ops()
+    rng = np.random.default_rng(scale)
+    t = rng.integers(0, scale, size=(n, 4))
+    t[::3, 1] *= rng.integers(1, 20)
+    t[::5, 2] //= 3
+    got = ops.fisher_tables(t[:, 0], t[:, 1], t[:, 2], t[:, 3]).cpu().numpy()
+    want = fisher_c.fisher_two_sided(t[:, 0], t[:, 1], t[:, 2], t[:, 3])
+    _check(got, want, rtol=1e-11)
+
+
+def test_pairwise_layout_and_exclusions():
+    """inc/exc matrices -> [J, P] with the reference's pair order (pairwise_fisher.py:142-145)."""
+    _, ops = _ops()
+    J, S = 3000, 12
+    _, csr, counts = util.synthetic_problem(J, S, seed=11, zero_frac=0.1)
+    exc = oracle_np.exclusion_sums(counts, csr["row_ptr"], csr["col_idx"])
+    pa, pb = oracle_np.all_pairs(S)
+    dev = torch.device("cuda", 0)
+    got = ops.fisher_pairwise(torch.from_numpy(counts).to(dev), torch.from_numpy(exc).to(dev), pa, pb).cpu().numpy()
+    want = fisher_c.pairwise(counts, exc, pa, pb)
+    assert got.shape == (J, S * (S - 1) // 2)
+    _check(got.ravel(), want.ravel(), rtol=1e-11)
+    # rows with an empty adjacency list have a zero margin: p = 1 everywhere
+    empty = np.diff(csr["row_ptr"]) == 0
+    assert empty.any() and np.all(got[empty] == 1.0)
+    # host-buffer entry point, ragged row range
+    got_h = ops.fisher_pairwise_host(counts, exc, pa, pb).numpy()
+    np.testing.assert_array_equal(got_h, got)
+
+
+def test_negative_entries_are_rejected():
+    native, ops = _ops()
+    with pytest.raises(native.NativeCallError):
+        ops.fisher_tables([1, 2], [3, -1], [4, 4], [5, 5])
+
+
+def test_survey_vector_pairwise_file(golden_dir):
+    """SURVEY.md section 4 known-answer vector, values taken from the reference's own output file."""
+    import os
+    _, ops = _ops()
+    path = os.path.join(golden_dir, "survey_vector", "expected", "pairwise_none.tsv")
+    rows = [l.rstrip("\n").split("\t") for l in open(path)]
+    want = np.array([[float(x) for x in r[1:]] for r in rows[1:]])
+    cpath = os.path.join(golden_dir, "survey_vector", "expected", "ref_inclusionCounts.tsv")
+    crow = [l.rstrip("\n").split("\t") for l in open(cpath)][1:]
+    names = [r[0] for r in crow]
+    counts = np.array([[int(x) for x in r[1:]] for r in crow], dtype=np.int32)
+    adj = {}
+    for l in open(os.path.join(golden_dir, "survey_vector", "expected", "ref_allClusters.tsv")):
+        f = l.rstrip("\n").split("\t")
+        adj[f[0]] = [x for x in f[1].split(",") if x] if len(f) > 1 else []
+    idx = {n: i for i, n in enumerate(names)}
+    exc = np.array([counts[[idx[o] for o in adj[n]]].sum(axis=0) if adj[n] else np.zeros(3, int) for n in names],
+                   dtype=np.int64)
+    pa, pb = oracle_np.all_pairs(3)
+    dev = torch.device("cuda", 0)
+    got = ops.fisher_pairwise(torch.from_numpy(counts).to(dev), torch.from_numpy(exc).to(dev), pa, pb).cpu().numpy()
+    by_name = {r[0]: i for i, r in enumerate(rows[1:])}
+    order = [by_name[n] for n in names]
+    np.testing.assert_allclose(got, want[order], rtol=RTOL, atol=0)

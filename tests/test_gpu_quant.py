@@ -1,0 +1,121 @@
+"""K2 parity on the GPU: exclusion sums and PS against the oracle and the reference-made goldens."""
+import numpy as np
+import pytest
+
+from oracle import oracle_np
+from tests import util
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def _ops():
+    from splicedice_b200 import native, ops
+    ops.require_cuda()
+    return native, ops
+
+
+def _run(counts, csr, low=None, flags=0, f64=True):
+    native, ops = _ops()
+    dev = torch.device("cuda", 0)
+    c = torch.from_numpy(counts.astype(np.int32)).to(dev)
+    m = None if low is None else torch.from_numpy(low.astype(np.uint8)).to(dev)
+    r = ops.quant_ps(c, csr["row_ptr"], csr["col_idx"], low_mask=m, want_f32=True, want_f64=f64, want_exc=True,
+                     flags=flags)
+    torch.cuda.synchronize()
+    return {k: (None if v is None else v.cpu().numpy()) for k, v in r.items()}
+
+
+@pytest.mark.parametrize("name", ["quant_adversarial.npz", "quant_synth_3k.npz"])
+@pytest.mark.parametrize("variant", ["tiled", "gather"])
+def test_golden_ps_bits(name, variant):
+    """float32 PS bit-for-bit (NaN payloads included) vs SPLICEDICE.calculatePsi run on the reference."""
+    native, _ = _ops()
+    g = util.load_npz(name)
+    counts = g["counts"]
+    csr = dict(row_ptr=g["row_ptr"].astype(np.int32), col_idx=g["col_idx"].astype(np.int32))
+    flags = native.SD_QUANT_TILED if variant == "tiled" else native.SD_QUANT_GATHER
+    got = _run(counts, csr, flags=flags)
+    np.testing.assert_array_equal(util.bits32(got["ps_f32"]), g["psi_nolow_bits"])
+    low = np.zeros(counts.shape, dtype=np.uint8)
+    low[g["low"][:, 0], g["low"][:, 1]] = 1
+    got = _run(counts, csr, low=low, flags=flags)
+    np.testing.assert_array_equal(util.bits32(got["ps_f32"]), g["psi_bits"])
+    np.testing.assert_array_equal(got["exc"], oracle_np.exclusion_sums(counts, csr["row_ptr"], csr["col_idx"]))
+
+
+@pytest.mark.parametrize("shape", [(5000, 8), (3000, 64), (2500, 130), (1200, 1000), (700, 1001), (64, 3), (1, 1),
+                                   (4000, 260)])
+@pytest.mark.parametrize("variant", ["tiled", "gather"])
+def test_oracle_parity(shape, variant):
+    native, ops = _ops()
+    J, S = shape
+    _, csr, counts = util.synthetic_problem(J, S, seed=J + S)
+    dev = torch.device("cuda", 0)
+    # pad the leading dimension to a multiple of 4 so that the tiled kernel applies to any S
+    ld = (S + 3) // 4 * 4 if variant == "tiled" else S
+    buf = torch.zeros((J, ld), dtype=torch.int32, device=dev)
+    buf[:, :S] = torch.from_numpy(counts).to(dev)
+    view = buf[:, :S]
+    flags = native.SD_QUANT_TILED if variant == "tiled" else native.SD_QUANT_GATHER
+    r = ops.quant_ps(view, csr["row_ptr"], csr["col_idx"], want_f32=True, want_f64=True, want_exc=True, flags=flags)
+    torch.cuda.synchronize()
+    exc = oracle_np.exclusion_sums(counts, csr["row_ptr"], csr["col_idx"])
+    np.testing.assert_array_equal(r["exc"].cpu().numpy(), exc)
+    want32 = oracle_np.ps_f32(counts, csr["row_ptr"], csr["col_idx"], exc=exc)
+    want64 = oracle_np.ps_f64(counts, csr["row_ptr"], csr["col_idx"], exc=exc)
+    np.testing.assert_array_equal(util.bits32(r["ps_f32"].cpu().numpy()), util.bits32(want32))
+    np.testing.assert_array_equal(util.bits64(r["ps_f64"].cpu().numpy()), util.bits64(want64))
+
+
+def test_large_counts_take_the_f64_path():
+    """Totals above 2^24 must still equal float32(float64 divide)."""
+    native, ops = _ops()
+    J, S = 600, 40
+    _, csr, counts = util.synthetic_problem(J, S, seed=5)
+    rng = np.random.default_rng(0)
+    counts = (counts.astype(np.int64) * rng.integers(1, 400000, size=counts.shape)).clip(0, 2 ** 31 - 1).astype(np.int32)
+    got = _run(counts, csr)
+    exc = oracle_np.exclusion_sums(counts, csr["row_ptr"], csr["col_idx"])
+    np.testing.assert_array_equal(got["exc"], exc)
+    inc = counts.astype(np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        want = (inc / (inc + exc)).astype(np.float32)
+    np.testing.assert_array_equal(util.bits32(got["ps_f32"]), util.bits32(want))
+
+
+def test_row_ranges_and_empty():
+    native, ops = _ops()
+    J, S = 900, 24
+    _, csr, counts = util.synthetic_problem(J, S, seed=77)
+    dev = torch.device("cuda", 0)
+    c = torch.from_numpy(counts).to(dev)
+    out = torch.full((J, S), -5.0, dtype=torch.float32, device=dev)
+    ops.quant_ps(c, csr["row_ptr"], csr["col_idx"], out_f32=out, row_begin=100, row_end=333)
+    ops.quant_ps(c, csr["row_ptr"], csr["col_idx"], out_f32=out, row_begin=333, row_end=333)   # empty range
+    torch.cuda.synchronize()
+    want = oracle_np.ps_f32(counts, csr["row_ptr"], csr["col_idx"])
+    got = out.cpu().numpy()
+    np.testing.assert_array_equal(util.bits32(got[100:333]), util.bits32(want[100:333]))
+    assert (got[:100] == -5.0).all() and (got[333:] == -5.0).all()
+    with pytest.raises(native.NativeCallError):
+        ops.quant_ps(c, csr["row_ptr"], csr["col_idx"], row_begin=5, row_end=J + 1)
+
+
+def test_host_pipeline_matches_device_path():
+    native, ops = _ops()
+    J, S = 20000, 333
+    _, csr, counts = util.synthetic_problem(J, S, seed=3)
+    low = (np.random.default_rng(1).random((J, S)) < 0.01).astype(np.uint8)
+    pinned = torch.from_numpy(counts).pin_memory()
+    out = ops.quant_ps_host(pinned, csr["row_ptr"], csr["col_idx"], low_mask=low).numpy()
+    want = oracle_np.ps_f32(counts, csr["row_ptr"], csr["col_idx"], low_mask=low)
+    np.testing.assert_array_equal(util.bits32(out), util.bits32(want))
+
+
+def test_device_synth_matches_host_generator():
+    native, ops = _ops()
+    from splicedice_b200 import synth
+    got = ops.synth_counts(seed=9, row0=1000, n_rows=257, n_cols=1000, logical_cols=1000).cpu().numpy()
+    want = synth.counts_host(9, 1000, 257, 1000)
+    np.testing.assert_array_equal(got, want)
