@@ -22,7 +22,9 @@ def require_cuda():
 
 def _dev(device=None):
     require_cuda()
-    return torch.device("cuda", torch.cuda.current_device() if device is None else device)
+    if isinstance(device, torch.device):
+        return device if device.index is not None else torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
 
 
 def _i32(x, device):

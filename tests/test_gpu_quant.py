@@ -18,7 +18,11 @@ def _ops():
 def _run(counts, csr, low=None, flags=0, f64=True):
     native, ops = _ops()
     dev = torch.device("cuda", 0)
-    c = torch.from_numpy(counts.astype(np.int32)).to(dev)
+    J, S = counts.shape
+    # leading dimension padded to a multiple of 4 elements: the tiled kernel's 16-byte row alignment
+    buf = torch.zeros((J, (S + 3) // 4 * 4), dtype=torch.int32, device=dev)
+    buf[:, :S] = torch.from_numpy(counts.astype(np.int32)).to(dev)
+    c = buf[:, :S]
     m = None if low is None else torch.from_numpy(low.astype(np.uint8)).to(dev)
     r = ops.quant_ps(c, csr["row_ptr"], csr["col_idx"], low_mask=m, want_f32=True, want_f64=f64, want_exc=True,
                      flags=flags)
