@@ -123,3 +123,86 @@ def test_device_synth_matches_host_generator():
     got = ops.synth_counts(seed=9, row0=1000, n_rows=257, n_cols=1000, logical_cols=1000).cpu().numpy()
     want = synth.counts_host(9, 1000, 257, 1000)
     np.testing.assert_array_equal(got, want)
+
+
+def test_small_divide_exhaustive_and_random():
+    """The float32 fast path (div_small) against float32(float64 a / float64 b): every pair
+    0 <= a <= b <= 2048 and 4M random pairs with b <= 2^24, through both wide instantiations."""
+    native, ops = _ops()
+    b = np.repeat(np.arange(1, 2049), np.arange(2, 2050))
+    a = np.concatenate([np.arange(0, k + 1) for k in range(1, 2049)])
+    rng = np.random.default_rng(4)
+    rb = rng.integers(1, 2 ** 24 + 1, size=4_000_000)
+    ra = (rng.random(rb.size) * (rb + 1)).astype(np.int64).clip(0, rb)
+    edge = np.array([[2 ** 24, 2 ** 24], [2 ** 24 - 1, 2 ** 24], [1, 2 ** 24], [0, 2 ** 24], [2 ** 23 + 1, 2 ** 24 - 1]])
+    a = np.concatenate([a, ra, edge[:, 0]]); b = np.concatenate([b, rb, edge[:, 1]])
+    S = 1024
+    pad = (-a.size) % S
+    a = np.concatenate([a, np.zeros(pad, dtype=np.int64)]); b = np.concatenate([b, np.ones(pad, dtype=np.int64)])
+    M = a.size // S
+    counts = np.empty((2 * M, S), dtype=np.int32)
+    counts[0::2] = a.reshape(M, S)
+    counts[1::2] = (b - a).reshape(M, S)
+    row_ptr = np.arange(2 * M + 1, dtype=np.int32)
+    col_idx = (np.arange(2 * M, dtype=np.int32) ^ 1)
+    dev = torch.device("cuda", 0)
+    c = torch.from_numpy(counts).to(dev)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        want = (counts.astype(np.float64) / np.repeat(b.reshape(M, S), 2, axis=0)).astype(np.float32)
+    lean = ops.quant_ps(c, row_ptr, col_idx)["ps_f32"].cpu().numpy()
+    np.testing.assert_array_equal(util.bits32(lean), util.bits32(want))
+    general = ops.quant_ps(c, row_ptr, col_idx, want_exc=True)["ps_f32"].cpu().numpy()
+    np.testing.assert_array_equal(util.bits32(general), util.bits32(want))
+
+
+@pytest.mark.parametrize("log_r", [3, 5, 7])
+def test_wide_kernel_tile_shapes_and_unstaged_adjacency(log_r):
+    """Deep nests (adjacency of one tile larger than the staging buffer) and other tile heights."""
+    native, ops = _ops()
+    from splicedice_b200 import synth
+    js = [("chr1", 1000, 900000, "+")] + [("chr1", 2000 + 40 * i, 2030 + 40 * i, "+") for i in range(3000)]
+    js += synth.junction_tuples(2000, 5)
+    c, s, st, en, _, _ = oracle_np.junctions_to_arrays(js)
+    csr = oracle_np.cluster_csr(c, s, st, en)
+    J, S = len(js), 200
+    counts = synth.counts_host(3, 0, J, S)
+    dev = torch.device("cuda", 0)
+    r = ops.quant_ps(torch.from_numpy(counts).to(dev), csr["row_ptr"], csr["col_idx"], want_exc=True,
+                     flags=native.SD_QUANT_TILED | (log_r << 8))
+    exc = oracle_np.exclusion_sums(counts, csr["row_ptr"], csr["col_idx"])
+    np.testing.assert_array_equal(r["exc"].cpu().numpy(), exc)
+    want = oracle_np.ps_f32(counts, csr["row_ptr"], csr["col_idx"], exc=exc)
+    np.testing.assert_array_equal(util.bits32(r["ps_f32"].cpu().numpy()), util.bits32(want))
+    lean = ops.quant_ps(torch.from_numpy(counts).to(dev), csr["row_ptr"], csr["col_idx"],
+                        flags=native.SD_QUANT_TILED | (log_r << 8))["ps_f32"].cpu().numpy()
+    np.testing.assert_array_equal(util.bits32(lean), util.bits32(want))
+
+
+def test_narrow_tile_kernel_on_wide_matrix():
+    native, ops = _ops()
+    J, S = 1500, 300
+    _, csr, counts = util.synthetic_problem(J, S, seed=8)
+    dev = torch.device("cuda", 0)
+    r = ops.quant_ps(torch.from_numpy(counts).to(dev), csr["row_ptr"], csr["col_idx"], want_exc=True,
+                     flags=native.SD_QUANT_TILED | native.SD_QUANT_NARROW_TILES)
+    want = oracle_np.ps_f32(counts, csr["row_ptr"], csr["col_idx"])
+    np.testing.assert_array_equal(util.bits32(r["ps_f32"].cpu().numpy()), util.bits32(want))
+
+
+def test_sums_beyond_32_bits_take_the_wide_path():
+    """Counts near 2^31 with several neighbours: exclusion sums exceed 2^32 and must stay exact."""
+    native, ops = _ops()
+    J, S = 400, 160
+    _, csr, counts = util.synthetic_problem(J, S, seed=12)
+    rng = np.random.default_rng(3)
+    big = rng.integers(2 ** 30, 2 ** 31 - 1, size=counts.shape)
+    counts = np.where(rng.random(counts.shape) < 0.5, big, counts).astype(np.int32)
+    got = _run(counts, csr)
+    exc = oracle_np.exclusion_sums(counts, csr["row_ptr"], csr["col_idx"])
+    assert exc.max() > 2 ** 32
+    np.testing.assert_array_equal(got["exc"], exc)
+    inc = counts.astype(np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        want64 = inc / (inc + exc)
+    np.testing.assert_array_equal(util.bits64(got["ps_f64"]), util.bits64(want64))
+    np.testing.assert_array_equal(util.bits32(got["ps_f32"]), util.bits32(want64.astype(np.float32)))
