@@ -20,20 +20,33 @@
 
 namespace sd {
 
+// kMode 0: every index is inside the staged shared-memory prefix; 1: shared prefix + global
+// table; 2: as 1, plus lgamma() beyond the table cap.
+__device__ __noinline__ double lgfact_fallback(double k) { return lgamma(k + 1.0); }
+
+template <int kMode>
 struct DeviceTable {
     const double2 *smem;     // staged prefix
     const double2 *gmem;     // full table
     int64_t n_smem, n_gmem;
-    __device__ __forceinline__ double2 load(int64_t k) const
+    template <class Int>
+    __device__ __forceinline__ double2 load(Int k) const
     {
-        if (k < n_smem) return smem[k];
-        if (k < n_gmem) return __ldg(gmem + k);
-        return make_double2(lgamma((double)k + 1.0), 0.0);
+        if (kMode == 0) return smem[k];
+        if ((int64_t)k < n_smem) return smem[k];
+        if (kMode == 1 || (int64_t)k < n_gmem) return __ldg(gmem + k);
+        return make_double2(lgfact_fallback((double)k), 0.0);
     }
-    __device__ __forceinline__ double hi(int64_t k) const { return load(k).x; }
-    __device__ __forceinline__ fisher::dd get(int64_t k) const
+    template <class Int>
+    __device__ __forceinline__ double hi(Int k) const
     {
-        double2 v = load(k);
+        if (kMode == 0) return reinterpret_cast<const double *>(smem)[2 * (int64_t)k];
+        return load(k).x;
+    }
+    template <class Int>
+    __device__ __forceinline__ fisher::dd get(Int k) const
+    {
+        const double2 v = load(k);
         return fisher::dd_make(v.x, v.y);
     }
 };
@@ -63,29 +76,39 @@ __device__ __forceinline__ void stage_table(double2 *s_tab, const double2 *g_tab
     __syncthreads();
 }
 
+template <class Int, int kMode>
 __global__ void __launch_bounds__(kFisherThreads, 2) fisher_pairwise_kernel(const FisherParams p)
 {
     extern __shared__ __align__(16) double2 s_tab[];
     stage_table(s_tab, p.table, p.smem_entries);
-    const DeviceTable tab{s_tab, p.table, p.smem_entries, p.table_entries};
+    const DeviceTable<kMode> tab{s_tab, p.table, p.smem_entries, p.table_entries};
 
     const int lane = threadIdx.x & 31;
     const int64_t tiles_per_row = (p.n_pairs + 31) / 32;
     const int64_t n_items = (p.row_end - p.row_begin) * tiles_per_row;
     const int64_t warp0 = (int64_t)blockIdx.x * (kFisherThreads / 32) + (threadIdx.x >> 5);
     const int64_t n_warps = (int64_t)gridDim.x * (kFisherThreads / 32);
+    // (row, tile) of the first item and the per-iteration advance, so the loop has no division
+    int64_t j = p.row_begin + warp0 / tiles_per_row;
+    int64_t t = warp0 % tiles_per_row;
+    const int64_t dj = n_warps / tiles_per_row, dt = n_warps % tiles_per_row;
     for (int64_t item = warp0; item < n_items; item += n_warps) {
-        const int64_t j = p.row_begin + item / tiles_per_row;
-        const int64_t k = (item % tiles_per_row) * 32 + lane;
-        if (k >= p.n_pairs) continue;
-        const int sa = __ldg(p.pair_a + k), sb = __ldg(p.pair_b + k);
-        const int64_t a = __ldg(p.inc + j * p.ld_inc + sa), b = __ldg(p.inc + j * p.ld_inc + sb);
-        const int64_t c = __ldg(p.exc + j * p.ld_exc + sa), d = __ldg(p.exc + j * p.ld_exc + sb);
-        const double pv = fisher::two_sided(tab, a, b, c, d);
-        __stcs(p.p_out + j * p.ld_p + k, pv);
+        const int64_t k = t * 32 + lane;
+        if (k < p.n_pairs) {
+            const int sa = __ldg(p.pair_a + k), sb = __ldg(p.pair_b + k);
+            const int32_t *inc = p.inc + j * p.ld_inc;
+            const int64_t *exc = p.exc + j * p.ld_exc;
+            const Int a = (Int)__ldg(inc + sa), b = (Int)__ldg(inc + sb);
+            const Int c = (Int)__ldg(exc + sa), d = (Int)__ldg(exc + sb);
+            __stcs(p.p_out + j * p.ld_p + k, fisher::two_sided<Int>(tab, a, b, c, d));
+        }
+        j += dj;
+        t += dt;
+        if (t >= tiles_per_row) { t -= tiles_per_row; ++j; }
     }
 }
 
+template <class Int, int kMode>
 __global__ void __launch_bounds__(kFisherThreads, 2) fisher_tables_kernel(
     int64_t n, const int64_t *__restrict__ a, const int64_t *__restrict__ b,
     const int64_t *__restrict__ c, const int64_t *__restrict__ d, double *__restrict__ out,
@@ -93,10 +116,10 @@ __global__ void __launch_bounds__(kFisherThreads, 2) fisher_tables_kernel(
 {
     extern __shared__ __align__(16) double2 s_tab[];
     stage_table(s_tab, table, smem_entries);
-    const DeviceTable tab{s_tab, table, smem_entries, table_entries};
+    const DeviceTable<kMode> tab{s_tab, table, smem_entries, table_entries};
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        out[i] = fisher::two_sided(tab, a[i], b[i], c[i], d[i]);
+        out[i] = fisher::two_sided<Int>(tab, (Int)a[i], (Int)b[i], (Int)c[i], (Int)d[i]);
 }
 
 // max over the row range of inc + exc (pairwise) or of a + b + c + d (tables); also flags
@@ -209,29 +232,77 @@ static int fisher_grid(const void *kernel, size_t smem)
     return sms * per_sm;
 }
 
-int launch_fisher_pairwise(FisherParams p, cudaStream_t stream)
+// instantiation for (largest table total, table coverage)
+template <template <class, int> class Launcher, class... Args>
+static int dispatch(int64_t max_total, int64_t smem_entries, int64_t table_entries, Args... args)
 {
-    // table size: the largest table total in the row range is at most 2 * max(inc + exc)
+    const bool small = max_total < (int64_t(1) << 30);
+    const int mode = max_total < smem_entries ? 0 : (max_total < table_entries ? 1 : 2);
+    if (small) {
+        if (mode == 0) return Launcher<int32_t, 0>::run(args...);
+        if (mode == 1) return Launcher<int32_t, 1>::run(args...);
+        return Launcher<int32_t, 2>::run(args...);
+    }
+    if (mode == 1) return Launcher<int64_t, 1>::run(args...);
+    return Launcher<int64_t, 2>::run(args...);
+}
+
+template <class Int, int kMode>
+struct PairwiseLauncher {
+    static int run(const FisherParams &p, cudaStream_t stream)
+    {
+        auto kernel = fisher_pairwise_kernel<Int, kMode>;
+        const size_t smem = (size_t)p.smem_entries * sizeof(double2);
+        SD_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)(kSmemEntriesMax * sizeof(double2))));
+        const int64_t items = (p.row_end - p.row_begin) * ((p.n_pairs + 31) / 32);
+        int grid = fisher_grid((const void *)kernel, smem);
+        grid = (int)std::min<int64_t>(grid, (items + kFisherThreads / 32 - 1) / (kFisherThreads / 32));
+        kernel<<<grid, kFisherThreads, smem, stream>>>(p);
+        return check_launch("fisher_pairwise_kernel");
+    }
+};
+
+template <class Int, int kMode>
+struct TablesLauncher {
+    static int run(int64_t n, const int64_t *a, const int64_t *b, const int64_t *c, const int64_t *d, double *out,
+                   const double2 *table, int64_t entries, int32_t smem_entries, cudaStream_t stream)
+    {
+        auto kernel = fisher_tables_kernel<Int, kMode>;
+        const size_t smem = (size_t)smem_entries * sizeof(double2);
+        SD_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)(kSmemEntriesMax * sizeof(double2))));
+        int grid = fisher_grid((const void *)kernel, smem);
+        grid = (int)std::min<int64_t>(grid, (n + kFisherThreads - 1) / kFisherThreads);
+        kernel<<<grid, kFisherThreads, smem, stream>>>(n, a, b, c, d, out, table, entries, smem_entries);
+        return check_launch("fisher_tables_kernel");
+    }
+};
+
+// max over rows [row_begin, row_end) of inc + exc (a table total is at most twice that);
+// SD_ERR_INVALID on a negative entry.  Synchronises the stream.
+int fisher_max_cell(const FisherParams &p, cudaStream_t stream, int64_t *max_cell)
+{
     unsigned long long *d_max = nullptr;
     SD_CHECK_CUDA(cudaMallocAsync(&d_max, 16, stream));
     SD_CHECK_CUDA(cudaMemsetAsync(d_max, 0, 16, stream));
     int *d_neg = reinterpret_cast<int *>(d_max + 1);
     const int64_t cells = (p.row_end - p.row_begin) * p.n_samples;
     fisher_scan_pairwise<<<(int)std::min<int64_t>((cells + 255) / 256, kSMs * 8), 256, 0, stream>>>(p, d_max, d_neg);
-    int64_t max_cell = 0;
-    int rc = scan_result(d_max, d_neg, stream, &max_cell, "sd_fisher_pairwise");
+    int rc = scan_result(d_max, d_neg, stream, max_cell, "sd_fisher_pairwise");
     cudaFreeAsync(d_max, stream);
-    if (rc != SD_OK) return rc;
-    if ((rc = device_table(2 * max_cell + 2, &p.table, &p.table_entries, stream)) != SD_OK) return rc;
-    p.smem_entries = (int32_t)std::min<int64_t>(std::min<int64_t>(2 * max_cell + 2, p.table_entries), kSmemEntriesMax);
-    const size_t smem = (size_t)p.smem_entries * sizeof(double2);
-    SD_CHECK_CUDA(cudaFuncSetAttribute(fisher_pairwise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(kSmemEntriesMax * sizeof(double2))));
-    const int64_t items = (p.row_end - p.row_begin) * ((p.n_pairs + 31) / 32);
-    int grid = fisher_grid((const void *)fisher_pairwise_kernel, smem);
-    grid = (int)std::min<int64_t>(grid, (items + kFisherThreads / 32 - 1) / (kFisherThreads / 32));
-    fisher_pairwise_kernel<<<grid, kFisherThreads, smem, stream>>>(p);
-    return check_launch("fisher_pairwise_kernel");
+    return rc;
+}
+
+// max_cell < 0: measure it first (one stream synchronisation)
+int launch_fisher_pairwise(FisherParams p, cudaStream_t stream, int64_t max_cell)
+{
+    if (max_cell < 0)
+        if (int rc = fisher_max_cell(p, stream, &max_cell)) return rc;
+    const int64_t max_total = 2 * max_cell;
+    if (int rc = device_table(max_total + 1, &p.table, &p.table_entries, stream)) return rc;
+    p.smem_entries = (int32_t)std::min<int64_t>(std::min<int64_t>(max_total + 1, p.table_entries), kSmemEntriesMax);
+    return dispatch<PairwiseLauncher>(max_total, p.smem_entries, p.table_entries, p, stream);
 }
 
 }  // namespace sd
@@ -254,7 +325,7 @@ int sd_fisher_pairwise(int64_t n_junctions, int32_t n_samples, const int32_t *in
     p.inc = inc; p.ld_inc = ld_inc; p.exc = exc; p.ld_exc = ld_exc;
     p.n_pairs = n_pairs; p.pair_a = pair_a; p.pair_b = pair_b;
     p.p_out = p_out; p.ld_p = ld_p; p.row_begin = row_begin; p.row_end = row_end;
-    return sd::launch_fisher_pairwise(p, (cudaStream_t)stream);
+    return sd::launch_fisher_pairwise(p, (cudaStream_t)stream, -1);
 }
 
 int sd_fisher_tables(int64_t n_tables, const int64_t *a, const int64_t *b, const int64_t *c,
@@ -279,14 +350,8 @@ int sd_fisher_tables(int64_t n_tables, const int64_t *a, const int64_t *b, const
     if ((rc = sd::device_table(max_total + 1, &table, &entries, stream)) != SD_OK) return rc;
     const int32_t smem_entries =
         (int32_t)std::min<int64_t>(std::min<int64_t>(max_total + 1, entries), sd::kSmemEntriesMax);
-    const size_t smem = (size_t)smem_entries * sizeof(double2);
-    SD_CHECK_CUDA(cudaFuncSetAttribute(sd::fisher_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(sd::kSmemEntriesMax * sizeof(double2))));
-    int grid = sd::fisher_grid((const void *)sd::fisher_tables_kernel, smem);
-    grid = (int)std::min<int64_t>(grid, (n_tables + sd::kFisherThreads - 1) / sd::kFisherThreads);
-    sd::fisher_tables_kernel<<<grid, sd::kFisherThreads, smem, stream>>>(n_tables, a, b, c, d, p_out, table,
-                                                                        entries, smem_entries);
-    return sd::check_launch("fisher_tables_kernel");
+    return sd::dispatch<sd::TablesLauncher>(max_total, (int64_t)smem_entries, entries, n_tables, a, b, c, d, p_out, table,
+                                            entries, smem_entries, stream);
 }
 
 // Host-buffer form: inc / exc / pairs / p_out are HOST pointers.  Row blocks of p-values are
@@ -350,6 +415,14 @@ int sd_fisher_pairwise_host(int device, int64_t n_junctions, int32_t n_samples, 
     SD_TRY(cudaMemcpyAsync(d_pa, pair_a, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, s_k));
     SD_TRY(cudaMemcpyAsync(d_pb, pair_b, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, s_k));
     const int64_t n_blocks = (J + block_rows - 1) / block_rows;
+    int64_t max_cell = 0;
+    {
+        sd::FisherParams all{};
+        all.n_samples = n_samples; all.inc = d_inc; all.ld_inc = n_samples; all.exc = d_exc; all.ld_exc = n_samples;
+        all.row_begin = 0; all.row_end = J;
+        rc = sd::fisher_max_cell(all, s_k, &max_cell);
+        if (rc != SD_OK) { cleanup(); return rc; }
+    }
     ev.resize((size_t)2 * n_blocks, nullptr);
     for (auto &e : ev) SD_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (int64_t b = 0; b < n_blocks; ++b) {
@@ -361,7 +434,7 @@ int sd_fisher_pairwise_host(int device, int64_t n_junctions, int32_t n_samples, 
         p.inc = d_inc; p.ld_inc = n_samples; p.exc = d_exc; p.ld_exc = n_samples;
         p.n_pairs = n_pairs; p.pair_a = d_pa; p.pair_b = d_pb;
         p.p_out = buf - r0 * n_pairs; p.ld_p = n_pairs; p.row_begin = r0; p.row_end = r1;
-        rc = sd::launch_fisher_pairwise(p, s_k);
+        rc = sd::launch_fisher_pairwise(p, s_k, max_cell);
         if (rc != SD_OK) { cleanup(); return rc; }
         SD_TRY(cudaEventRecord(ev[2 * b], s_k));
         SD_TRY(cudaStreamWaitEvent(s_out, ev[2 * b], 0));

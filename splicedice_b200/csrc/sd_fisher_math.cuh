@@ -16,7 +16,7 @@
 // 1 + r1 + r1 r2 + ... is the tail sum relative to its first term, accumulated with the exact
 // rational term ratio  pmf(x+1)/pmf(x) = (n1-x)(n-x) / ((x+1)(n2-n+x+1))  as a
 // numerator/denominator pair (no division in the loop) and cut when a term drops below
-// 2^-56 of the running sum.  pmf(a), t(g) and every "is pmf(x) within the tie window of
+// 2^-48 of the running sum.  pmf(a), t(g) and every "is pmf(x) within the tie window of
 // pmf(a)" decision come from a double-double log-factorial table (sd_lgtable.cpp).
 //
 // The header compiles for the device (sd_fisher.cu) and, without nvcc, for the host: the host
@@ -29,8 +29,10 @@
 
 #ifdef __CUDACC__
 #define SD_HD __host__ __device__ __forceinline__
+#define SD_NOINLINE __host__ __device__ __noinline__
 #else
 #define SD_HD inline
+#define SD_NOINLINE inline
 #endif
 
 namespace sd {
@@ -56,7 +58,7 @@ SD_HD dd dd_sub(dd x, dd y) { return dd_add(x, dd_make(-y.hi, -y.lo)); }
 constexpr double kEps = 1e-14;                          // scipy's epsilon (:5082)
 constexpr double kLogGamma = 9.992007221626358e-15;     // log(1 + 1e-14) with 1 + 1e-14 formed in binary64
 constexpr double kTieWindow = 1.0000000000000051e-14;   // -log(1 - 1e-14)
-constexpr double kCut = 1.3877787807814457e-17;         // 2^-56: tail truncation relative to the sum
+constexpr double kCut = 3.552713678800501e-15;          // 2^-48: tail truncation relative to the sum
 constexpr double kBig = 3.273390607896142e150;          // 2^500
 constexpr double kSmall = 3.054936363499605e-151;       // 2^-500
 
@@ -84,20 +86,21 @@ SD_HD double tail_sum(double p, double q, double u, double v)
 }
 
 // G(x) = lg[x] + lg[n1-x] + lg[n-x] + lg[n2-n+x]; log pmf(x) = const - G(x).
-template <class Table>
+// Int is the integer type of the table entries (int32_t when every table total fits 31 bits).
+template <class Table, class Int>
 struct Problem {
     const Table &tab;
-    int64_t n1, n2, n, N;
-    int64_t a, b, c, d;
+    Int n1, n2, n;
+    Int a, b, c, d;
     double tol;   // bound on the error of a hi-only evaluation of G(a) - G(x)
 
     // f(x) = log(pmf(x) / pmf(a)) from the hi words only
-    SD_HD double f_fast(int64_t x) const
+    SD_HD double f_fast(Int x) const
     {
         return (tab.hi(a) - tab.hi(x)) + (tab.hi(b) - tab.hi(n1 - x)) + (tab.hi(c) - tab.hi(n - x)) +
                (tab.hi(d) - tab.hi(n2 - n + x));
     }
-    SD_HD dd f_exact(int64_t x) const
+    SD_NOINLINE dd f_exact(Int x) const
     {
         dd s = dd_sub(tab.get(a), tab.get(x));
         s = dd_add(s, dd_sub(tab.get(b), tab.get(n1 - x)));
@@ -106,34 +109,44 @@ struct Problem {
         return s;
     }
     // scipy's far-side admission test: pmf(x) <= pexact * (1 + 1e-14)
-    SD_HD bool admitted(int64_t x) const
+    SD_HD bool admitted(Int x) const
     {
-        double f = f_fast(x);
+        const double f = f_fast(x);
         if (fabs(f - kLogGamma) > tol) return f < kLogGamma;
-        dd fe = f_exact(x);
+        const dd fe = f_exact(x);
         return fe.hi + fe.lo <= kLogGamma;
     }
 };
 
-template <class Table>
-SD_HD double two_sided(const Table &tab, int64_t a, int64_t b, int64_t c, int64_t d)
+template <class Int, class Table>
+SD_HD double two_sided(const Table &tab, Int a, Int b, Int c, Int d)
 {
-    const int64_t n1 = a + b, n2 = c + d, n = a + c, N = n1 + n2;
+    Int n1 = a + b, n2 = c + d, n = a + c;
     if (n1 == 0 || n2 == 0 || n == 0 || b + d == 0) return 1.0;
-    const int64_t lo = n - n2 > 0 ? n - n2 : 0;
-    const int64_t hi = n1 < n ? n1 : n;
+    const Int N = n1 + n2;
     // numpy: int64 product, float64 divide, int() truncation
-    const int64_t mode = (int64_t)((double)((n + 1) * (n1 + 1)) / (double)(N + 2));
+    Int mode = (Int)((double)((int64_t)(n + 1) * (int64_t)(n1 + 1)) / (double)((int64_t)N + 2));
     if (a == mode) return 1.0;
+    // Observed count above the mode: swap the columns.  x -> n1 - x maps the distribution onto
+    // hypergeom(N, n1, N - n) with identical pmf values, so from here on a < mode and the far
+    // side is the upper one.  (The reflected mode is only used as a point whose pmf exceeds
+    // pmf(a) * (1 + 1e-14), which the tie test below guarantees.)
+    if (a > mode) {
+        Int t = a; a = b; b = t;
+        t = c; c = d; d = t;
+        n = N - n;
+        mode = n1 - mode;
+    }
+    const Int hi = n1 < n ? n1 : n;
 
-    Problem<Table> pr{tab, n1, n2, n, N, a, b, c, d, 0.0};
+    Problem<Table, Int> pr{tab, n1, n2, n, a, b, c, d, 0.0};
     pr.tol = 64.0 * 2.220446049250313e-16 * (tab.hi(N) + 1.0);
 
     // tie between the observed table and the mode (plateau or mirror twin)
     {
-        double fm = pr.f_fast(mode);
+        const double fm = pr.f_fast(mode);
         if (fabs(fm) <= pr.tol + kTieWindow) {
-            dd fe = pr.f_exact(mode);
+            const dd fe = pr.f_exact(mode);
             if (fabs(fe.hi + fe.lo) <= kTieWindow) return 1.0;
         }
     }
@@ -147,91 +160,43 @@ SD_HD double two_sided(const Table &tab, int64_t a, int64_t b, int64_t c, int64_
     lp = dd_sub(lp, tab.get(b));
     lp = dd_sub(lp, tab.get(c));
     lp = dd_sub(lp, tab.get(d));
-    double pexact = exp(lp.hi);
-    pexact = fma(pexact, lp.lo, pexact);
 
-    double s_near, s_far = 0.0;
-    int64_t g;          // first admitted far-side point
-    bool have_far;
-    if (a < mode) {
-        s_near = tail_sum((double)a, (double)d, (double)b, (double)c);         // a, a-1, ... lo
-        // smallest g in (mode, hi] with admitted(g)
-        int64_t lo_x = mode, hi_x = hi + 1;
-        int64_t x = 2 * mode - a;
+    // smallest g in (mode, hi] with admitted(g): start from the mirror image of a, gallop, bisect
+    Int lo_x = mode, hi_x = hi + 1;
+    {
+        Int x = 2 * mode - a;
         if (x > hi) x = hi;
         if (x <= mode) x = mode + 1;
         if (x <= hi) {
-            int64_t step = 1;
-            if (pr.admitted(x)) {
-                hi_x = x;
-                while (true) {
-                    int64_t y = hi_x - step;
-                    if (y <= lo_x) break;
-                    if (pr.admitted(y)) { hi_x = y; step *= 2; }
-                    else { lo_x = y; break; }
-                }
-            } else {
-                lo_x = x;
-                while (true) {
-                    int64_t y = lo_x + step;
-                    if (y >= hi_x) break;
-                    if (pr.admitted(y)) { hi_x = y; break; }
-                    lo_x = y; step *= 2;
-                }
+            const bool up = !pr.admitted(x);        // true: the boundary is above x
+            if (up) lo_x = x; else hi_x = x;
+            Int step = 1;
+            while (true) {
+                const Int y = up ? lo_x + step : hi_x - step;
+                if (up ? y >= hi_x : y <= lo_x) break;
+                const bool adm = pr.admitted(y);
+                if (adm) hi_x = y; else lo_x = y;
+                if (adm == up) break;               // the boundary is bracketed
+                step *= 2;
             }
             while (hi_x - lo_x > 1) {
-                int64_t mid = lo_x + (hi_x - lo_x) / 2;
+                const Int mid = lo_x + (hi_x - lo_x) / 2;
                 if (pr.admitted(mid)) hi_x = mid; else lo_x = mid;
             }
         }
-        g = hi_x;
-        have_far = g <= hi;
-        if (have_far)
-            s_far = tail_sum((double)(n1 - g), (double)(n - g), (double)g, (double)(n2 - n + g));
-    } else {
-        s_near = tail_sum((double)b, (double)c, (double)a, (double)d);         // a, a+1, ... hi
-        // largest g in [lo, mode) with admitted(g)
-        int64_t lo_x = lo - 1, hi_x = mode;
-        int64_t x = 2 * mode - a;
-        if (x < lo) x = lo;
-        if (x >= mode) x = mode - 1;
-        if (x >= lo) {
-            int64_t step = 1;
-            if (pr.admitted(x)) {
-                lo_x = x;
-                while (true) {
-                    int64_t y = lo_x + step;
-                    if (y >= hi_x) break;
-                    if (pr.admitted(y)) { lo_x = y; step *= 2; }
-                    else { hi_x = y; break; }
-                }
-            } else {
-                hi_x = x;
-                while (true) {
-                    int64_t y = hi_x - step;
-                    if (y <= lo_x) break;
-                    if (pr.admitted(y)) { lo_x = y; break; }
-                    hi_x = y; step *= 2;
-                }
-            }
-            while (hi_x - lo_x > 1) {
-                int64_t mid = lo_x + (hi_x - lo_x) / 2;
-                if (pr.admitted(mid)) lo_x = mid; else hi_x = mid;
-            }
-        }
-        g = lo_x;
-        have_far = g >= lo;
-        if (have_far)
-            s_far = tail_sum((double)g, (double)(n2 - n + g), (double)(n1 - g), (double)(n - g));
     }
-    double rel = s_near;
-    if (have_far) {
-        dd fg = pr.f_exact(g);
+    const Int g = hi_x;
+    double rel = tail_sum((double)a, (double)d, (double)b, (double)c);           // a, a-1, ...
+    if (g <= hi) {
+        const double s_far = tail_sum((double)(n1 - g), (double)(n - g), (double)g, (double)(n2 - n + g));
+        const dd fg = pr.f_exact(g);
         double tg = exp(fg.hi);
         tg = fma(tg, fg.lo, tg);
-        rel = fma(tg, s_far, s_near);
+        rel = fma(tg, s_far, rel);
     }
-    double p = pexact * rel;
+    double pexact = exp(lp.hi);
+    pexact = fma(pexact, lp.lo, pexact);
+    const double p = pexact * rel;
     return p > 1.0 ? 1.0 : p;
 }
 

@@ -35,6 +35,6 @@ extern "C" int fisher_twin_batch(int64_t count, const int64_t *a, const int64_t 
     std::vector<double> tab;
     sd::lgtable_host(entries, &tab);
     HostTable T{tab.data(), entries};
-    for (int64_t i = 0; i < count; ++i) out[i] = sd::fisher::two_sided(T, a[i], b[i], c[i], d[i]);
+    for (int64_t i = 0; i < count; ++i) out[i] = (nmax < (int64_t(1) << 30) ? sd::fisher::two_sided<int32_t>(T, (int32_t)a[i], (int32_t)b[i], (int32_t)c[i], (int32_t)d[i]) : sd::fisher::two_sided<int64_t>(T, a[i], b[i], c[i], d[i]));
     return 0;
 }

@@ -50,7 +50,7 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 2
-        print(f"fisher {J}x{len(pa)}: {ms:.3f} ms/launch, {J * len(pa) / ms / 1e3:.3e} tests/s")
+        print(f"fisher {J}x{len(pa)}: {ms:.3f} ms/launch, {J * len(pa) / (ms * 1e-3):.3e} tests/s")
 
 
 if __name__ == "__main__":
