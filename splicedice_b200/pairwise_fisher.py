@@ -1,0 +1,133 @@
+"""``splicedice pairwise`` on a B200: per-event Fisher exact test for every sample pair.
+
+Host mirror of /root/reference/splicedice/pairwise_fisher.py (same flags, inputs and output
+file).  The hot loop (pairwise_fisher.py:154-180) runs on the GPU: exclusion counts with
+sd_quant_ps over the cluster CSR, then sd_fisher_pairwise for the [events x pairs] p-values.
+Benjamini-Hochberg and the writer stay on the host.  ``--chi2`` is not implemented (out of
+scope: BASELINE.json names the Fisher path only) and is rejected loudly.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import junctions as jn
+
+
+def getClusters(filename, filter_list=None):
+    """event -> list of mutually exclusive events.  Whitespace split; a line that is not exactly
+    two fields is an event with no partners (pairwise_fisher.py:26-43)."""
+    clusters = {}
+    with open(filename) as handle:
+        for line in handle:
+            fields = line.rstrip().split()
+            if len(fields) == 2:
+                clusters[fields[0]] = fields[1].split(",")
+            else:
+                clusters[line.strip()] = []
+    return clusters
+
+
+def getEventCounts(filename, filter_list=None):
+    """(sample names, event names, float64 counts); with a filter only listed events are kept."""
+    events, rows = [], []
+    with open(filename) as handle:
+        samples = handle.readline().rstrip().split("\t")[1:]
+        for line in handle:
+            row = line.rstrip().split("\t")
+            if filter_list is None or row[0] in filter_list:
+                events.append(row[0])
+                rows.append(row[1:])
+    return samples, events, np.array(rows, dtype=float)
+
+
+def fdr_bh(p):
+    """Benjamini-Hochberg adjusted p-values (statsmodels multipletests(method='fdr_bh')[1])."""
+    p = np.asarray(p, dtype=np.float64)
+    n = p.size
+    if n == 0:
+        return p.copy()
+    order = np.argsort(p, kind="stable")
+    scaled = p[order] / (np.arange(1, n + 1, dtype=np.float64) / float(n))
+    scaled = np.minimum.accumulate(scaled[::-1])[::-1]
+    scaled[scaled > 1] = 1
+    out = np.empty(n, dtype=np.float64)
+    out[order] = scaled
+    return out
+
+
+def sample_pairs(n_samples):
+    return [(i, j) for i in range(n_samples - 1) for j in range(i + 1, n_samples)]
+
+
+def pairwise_pvalues(events, counts, clusters, device=0):
+    """float64[len(events), n_pairs] two-sided Fisher p-values (uncorrected), pair order as
+    ``sample_pairs``."""
+    from . import ops
+    import torch
+    n_events, n_samples = counts.shape if counts.ndim == 2 else (0, 0)
+    pairs = sample_pairs(n_samples)
+    if n_events == 0 or not pairs:
+        return np.zeros((n_events, len(pairs)))
+    as_int = counts.astype(np.int64)                   # scipy truncates the table to int64 the same way
+    if (as_int < 0).any():
+        raise ValueError("All values in `table` must be nonnegative.")
+    if (as_int >= 2 ** 31).any():
+        raise ValueError("counts of 2^31 and above are not supported")
+    row_ptr, col_idx = jn.csr_from_named_lists(events, clusters, "isin")
+    dev = torch.device("cuda", device)
+    S = n_samples
+    buf = torch.zeros((n_events, (S + 3) // 4 * 4), dtype=torch.int32, device=dev)
+    buf[:, :S] = torch.from_numpy(as_int.astype(np.int32)).to(dev)
+    inc = buf[:, :S]
+    exc = ops.quant_ps(inc, row_ptr, col_idx, want_f32=False, want_exc=True)["exc"]
+    pa = np.array([a for a, _ in pairs], dtype=np.int32)
+    pb = np.array([b for _, b in pairs], dtype=np.int32)
+    return ops.fisher_pairwise(inc, exc, pa, pb).cpu().numpy()
+
+
+def add_parser(parser):
+    parser.add_argument("--inclusionSPLICEDICE", type=str, required=True,
+                        help="inclusionCounts.tsv written by quant")
+    parser.add_argument("-c", "--clusters", type=str, required=True, help="allClusters.tsv written by quant")
+    parser.add_argument("--chi2", action="store_true", default=False,
+                        help="(reference flag) chi-squared instead of Fisher -- not available on the GPU path")
+    parser.add_argument("--multiple_test_correction", default="pairwise", choices=["pairwise", "all", "none"],
+                        help="Benjamini-Hochberg per sample pair (default), over all p-values, or none")
+    parser.add_argument("-f", "--filter_list", help="text file of events to analyse, one per line")
+    parser.add_argument("-o", "--output", default="pairwise.tsv", help="output TSV")
+    parser.add_argument("--device", type=int, default=0, help="CUDA device ordinal")
+
+
+def run_with(args):
+    if args.chi2:
+        raise NotImplementedError("--chi2 is outside the B200 hot path (Fisher only); use the reference for it")
+    filter_list = None
+    if args.filter_list is not None:
+        with open(args.filter_list) as handle:
+            filter_list = {line.rstrip() for line in handle}
+    samples, events, counts = getEventCounts(args.inclusionSPLICEDICE, filter_list)
+    print("Counts loaded from", args.inclusionSPLICEDICE, "...")
+    clusters = getClusters(args.clusters, filter_list)
+    print("Clusters loaded from", args.clusters, "...")
+    pairs = sample_pairs(len(samples))
+    columns = [f"{samples[a]}_{samples[b]}" for a, b in pairs]
+    print("Analyzing pairs:")
+    print(",".join(columns))
+    parray = pairwise_pvalues(events, counts, clusters, getattr(args, "device", 0))
+    print(f"[{len(events)} / {len(events)}] events analyzed...")
+    if args.multiple_test_correction == "all":
+        parray = fdr_bh(parray.ravel()).reshape(parray.shape)
+    elif args.multiple_test_correction == "pairwise":
+        for k in range(parray.shape[1]):
+            parray[:, k] = fdr_bh(parray[:, k])
+    with open(args.output, "w") as out:
+        out.write("clusterID\t" + "\t".join(columns) + "\n")
+        for name, row in zip(events, parray):
+            out.write(name + "\t" + "\t".join(str(p) for p in row) + "\n")
+
+
+if __name__ == "__main__":
+    import argparse
+    cli = argparse.ArgumentParser(description="pairwise Fisher exact tests (B200)")
+    add_parser(cli)
+    run_with(cli.parse_args())

@@ -1,0 +1,318 @@
+"""``splicedice quant`` on a B200: host side of the reference's SPLICEDICE.py.
+
+Same command-line flags, manifest / sample-file formats and output files as
+/root/reference/splicedice/SPLICEDICE.py; the two compute stages run on the GPU through the
+C-ABI:
+
+    getClusters   (SPLICEDICE.py:230-255, row index :96)  -> sd_cluster_build / sd_cluster_fill
+    calculatePsi  (SPLICEDICE.py:297-310)                 -> sd_quant_ps_host
+
+File reading and the TSV writers stay host Python (they are I/O).
+Counts are held as int32 (the reference uses float32, exact below 2^24; scores of 2^24 and above
+are kept exact here where the reference would round them).
+"""
+from __future__ import annotations
+
+import os
+from time import time
+
+import numpy as np
+
+from . import junctions as jn
+
+BED_LIKE = ("bed", "splicedicebed", "leafcutter")
+_STRAND_OF_SJ = {"0": "0", "1": "+", "2": "-", "+": "+", "-": "-"}
+_MOTIF_SETS = {"gtag_only": {1, 2}, "gc_at": {1, 2, 3, 4, 5}, "all": {0, 1, 2, 3, 4, 5, 6}}
+
+
+class Sample:
+    """One manifest row; the file type is sniffed from the file name (SPLICEDICE.py:22-36)."""
+
+    def __init__(self, manifest_row):
+        self.name = manifest_row[0]
+        self.filename = manifest_row[1]
+        upper = self.filename.upper()
+        if upper.endswith(".BED"):
+            self.type = "bed"
+            with open(self.filename) as handle:
+                tags = handle.readline().split("\t")[3].split(";")
+            if tags[0].startswith("e:") and tags[1].startswith("o:"):
+                self.type = "splicedicebed"
+        elif upper.endswith("SJ.OUT.TAB"):
+            self.type = "SJ"
+        elif upper.endswith(".BAM"):
+            self.type = "bam"
+        elif upper.endswith("LEAFCUTTER.JUNC"):
+            self.type = "leafcutter"
+        else:
+            self.type = "unknown"
+        self.metadata = manifest_row[2]
+        self.condition = manifest_row[3]
+
+
+class Timer:
+    """Stage timer printing the reference's ``[h:mm:ss.ss]`` stamps (SPLICEDICE.py:48-66)."""
+
+    def __init__(self):
+        self.start = self.checkpoint = time()
+
+    @staticmethod
+    def _fmt(seconds):
+        return f"[{int(seconds // 3600)}:{int((seconds % 3600) // 60):02d}:{seconds % 60:02.2f}]"
+
+    def total(self):
+        return self._fmt(time() - self.start)
+
+    def check(self):
+        now = time()
+        out = self._fmt(now - self.checkpoint)
+        self.checkpoint = now
+        return out
+
+
+class SPLICEDICE:
+    """The quant pipeline.  Constructing it runs every stage, like the reference class; pass
+    ``run=False`` to drive the stages by hand (tests, library use)."""
+
+    def __init__(self, manifestFilename, outputPrefix, args, device=0, run=True):
+        self.args = args
+        self.manifestFilename = manifestFilename
+        self.outputPrefix = outputPrefix
+        self.device = device
+        self._csr = None
+        self._clusters = None
+        if run:
+            self.run()
+
+    # ---------------------------------------------------------------- pipeline ----------
+    def run(self):
+        timer = Timer()
+        print("Parsing manifest...")
+        self.manifest = self.parseManifest()
+        print("\tDone", timer.check())
+        print(f"Getting all junctions from {len(self.manifest)} files...")
+        self.junctions = self.getAllJunctions()
+        print("\tDone", timer.check())
+        print(f"Finding clusters from {len(self.junctions)} junctions...")
+        self.getClusters()
+        print("\tDone", timer.check())
+        print("Writing cluster file...")
+        self.writeClusters()
+        print("\tDone", timer.check())
+        print("Writing junction bed file...")
+        self.writeJunctionBed()
+        print("\tDone", timer.check())
+        print("Gathering junction counts...")
+        self.counts, self.low = self.getJunctionCounts()
+        print("\tDone", timer.check())
+        print("Writing inclusion counts...")
+        self.writeInclusions()
+        print("\tDone", timer.check())
+        print("Calculating PS values...")
+        self.psi = self.calculatePsi()
+        print("\tDone", timer.check())
+        print("Writing PS values...")
+        self.writeAllpsi()
+        print("\tDone", timer.check())
+        if self.args.drim:
+            print("Writing drim table...")
+            self.writeDrimTable()
+            print("\tDone", timer.check())
+        print("All done", timer.total())
+
+    def parseManifest(self):
+        """name, path, metadata, condition per line; no validation (SPLICEDICE.py:134-144)."""
+        with open(self.manifestFilename) as handle:
+            return [Sample(line.rstrip().split("\t")) for line in handle]
+
+    # ---------------------------------------------------------------- junction union ----
+    def _admit_sj(self, row):
+        a = self.args
+        left, right = int(row[1]) - 1, int(row[2])
+        strand = _STRAND_OF_SJ[row[3]]
+        score = int(row[6]) if a.noMultimap else int(row[6]) + int(row[7])
+        span = right - left
+        if (a.minLength < span < a.maxLength and strand != "0" and score >= a.minUnique
+                and int(row[4]) in self._motifs):
+            return (row[0], left, right, strand)
+        return None
+
+    def _admit_tagged_bed(self, row):
+        """bam_to_junc_bed output: the filters apply only to unannotated junctions (a:?)."""
+        a = self.args
+        score = int(row[4])
+        tags = [t.split(":") for t in row[3].split(";")]
+        left, right = int(row[1]), int(row[2])
+        if tags[3][1] == "?":
+            span = right - left
+            if (score < a.minUnique or span > a.maxLength or span < a.minLength
+                    or int(tags[1][1]) < a.minOverhang
+                    or float(tags[0][1]) < a.minEntropy or float(tags[0][2]) < a.minEntropy):
+                return None
+        return (row[0], left, right, row[5]) if row[5] in ("+", "-") else None
+
+    def _admit_plain_bed(self, row):
+        a = self.args
+        if int(row[4]) < a.minUnique:
+            return None
+        left, right = int(row[1]), int(row[2])
+        span = right - left
+        if span > a.maxLength or span < a.minLength:
+            return None
+        return (row[0], left, right, row[5]) if row[5] in ("+", "-") else None
+
+    def getAllJunctions(self):
+        """Union over samples of the junctions that pass that sample's filter
+        (SPLICEDICE.py:147-228).  ``.bam`` / unknown-suffix samples contribute nothing."""
+        self._motifs = _MOTIF_SETS[self.args.filter]
+        admit_by_type = {"SJ": self._admit_sj, "splicedicebed": self._admit_tagged_bed,
+                         "bed": self._admit_plain_bed, "leafcutter": self._admit_plain_bed}
+        found = set()
+        for sample in self.manifest:
+            with open(sample.filename) as handle:      # opened even when ignored, as the reference does
+                admit = admit_by_type.get(sample.type)
+                if admit is None:
+                    continue
+                for line in handle:
+                    j = admit(line.rstrip().split("\t"))
+                    if j is not None:
+                        found.add(j)
+        return found
+
+    # ---------------------------------------------------------------- clusters (GPU) ----
+    def getClusters(self):
+        """Overlap adjacency on the device.  Fills ``junctionIndex`` (tuple -> output row, the
+        order of ``sorted(junctions)``) and the CSR; returns the reference-shaped dict lazily via
+        ``self.clusters``."""
+        from . import ops
+        table = jn.JunctionTable(self.junctions)
+        built = ops.cluster_build(*table.arrays(), device=self.device)
+        out_row = built["out_row"].cpu().numpy()
+        self._rows = jn.rows_in_output_order(table.tuples, out_row)
+        self._csr = (built["row_ptr"].cpu().numpy(), built["col_idx"].cpu().numpy())
+        self.n_components = built["n_comp"]
+        self.junctionIndex = {j: r for r, j in enumerate(self._rows)}
+        self._clusters = None
+        return self.clusters
+
+    @property
+    def clusters(self):
+        if self._clusters is None and self._csr is not None:
+            self._clusters = jn.adjacency_dict(self._rows, *self._csr)
+        return self._clusters
+
+    # ---------------------------------------------------------------- counts -------------
+    def getJunctionCounts(self):
+        """int32[J, S] of scores (last duplicate line wins) and the list of low cells
+        (SPLICEDICE.py:257-295)."""
+        index = self.junctionIndex
+        a = self.args
+        counts = np.zeros((len(index), len(self.manifest)), dtype=np.int32)
+        low = []
+        for s, sample in enumerate(self.manifest):
+            with open(sample.filename) as handle:
+                if sample.type in BED_LIKE:
+                    for line in handle:
+                        row = line.rstrip().split("\t")
+                        r = index.get((row[0], int(row[1]), int(row[2]), row[5]))
+                        if r is None:
+                            continue
+                        score = int(row[4])
+                        counts[r, s] = score
+                        if a.lowCoverageNan and score < a.minUnique:
+                            low.append((r, s))
+                elif sample.type == "SJ":
+                    for line in handle:
+                        row = line.rstrip().split("\t")
+                        r = index.get((row[0], int(row[1]) - 1, int(row[2]), _STRAND_OF_SJ[row[3]]))
+                        if r is None:
+                            continue
+                        counts[r, s] = int(row[6]) if a.noMultimap else int(row[6]) + int(row[7])
+        return counts, low
+
+    # ---------------------------------------------------------------- PS (GPU) -----------
+    def calculatePsi(self):
+        """float32[J, S] PS in output-row order; NaN on zero coverage and, with
+        --lowCoverageNan, on the low cells (SPLICEDICE.py:297-310)."""
+        from . import ops
+        mask = None
+        if self.args.lowCoverageNan and self.low:
+            mask = np.zeros(self.counts.shape, dtype=np.uint8)
+            rows, cols = zip(*self.low)
+            mask[list(rows), list(cols)] = 1
+        row_ptr, col_idx = self._csr
+        if self.counts.size == 0:
+            return np.zeros(self.counts.shape, dtype=np.float32)
+        return ops.quant_ps_host(np.ascontiguousarray(self.counts, dtype=np.int32), row_ptr, col_idx,
+                                 low_mask=mask, device=self.device).numpy()
+
+    # ---------------------------------------------------------------- writers ------------
+    def junctionString(self, junction):
+        return jn.junction_name(junction)
+
+    def writeJunctionBed(self):
+        with open(f"{self.outputPrefix}_junctions.bed", "w") as out:
+            for chrom, left, right, strand in self._rows:
+                out.write(f"{chrom}\t{left}\t{right}\t{chrom}:{left}-{right}:{strand}\t0\t{strand}\n")
+
+    def writeClusters(self):
+        names = [jn.junction_name(j) for j in self._rows]
+        rp, ci = (x.tolist() for x in self._csr)
+        with open(f"{self.outputPrefix}_allClusters.tsv", "w") as out:
+            for r, name in enumerate(names):
+                out.write(name + "\t" + ",".join(names[c] for c in ci[rp[r]:rp[r + 1]]) + "\n")
+
+    def _write_matrix(self, path, matrix, fmt):
+        names = [jn.junction_name(j) for j in self._rows]
+        with open(path, "w") as out:
+            out.write("cluster\t" + "\t".join(s.name for s in self.manifest) + "\n")
+            for name, row in zip(names, matrix.tolist()):
+                out.write(name + "\t" + "\t".join(fmt(x) for x in row) + "\n")
+
+    def writeInclusions(self):
+        self._write_matrix(f"{self.outputPrefix}_inclusionCounts.tsv", self.counts, lambda x: f"{x:.0f}")
+
+    def writeAllpsi(self):
+        self._write_matrix(f"{self.outputPrefix}_allPS.tsv", self.psi, lambda x: f"{x:.3f}")
+
+    def writeDrimLine(self, i, junction, other, file):
+        # the reference prints its float32 counts with astype(str): "34.0"
+        values = "\t".join(f"{float(x)}" for x in self.counts[self.junctionIndex[other], :].tolist())
+        print(f"cl_{i}_{self.junctionString(junction)}", f"{self.junctionString(other)}_{i}", values,
+              sep="\t", file=file)
+
+    def writeDrimTable(self):
+        rp, ci = (x.tolist() for x in self._csr)
+        with open(f"{self.outputPrefix}_drimTable.tsv", "w") as out:
+            out.write("gene\tfeature_id\t" + "\t".join(s.name for s in self.manifest) + "\n")
+            for i, junction in enumerate(self._rows):
+                self.writeDrimLine(i, junction, junction, out)
+                for c in ci[rp[i]:rp[i + 1]]:
+                    self.writeDrimLine(i, junction, self._rows[c], out)
+
+
+def add_parser(parser):
+    parser.add_argument("--manifest", "-m", required=True,
+                        help="tab-separated sample list: name, path, metadata, condition")
+    parser.add_argument("--output_prefix", "-o", required=True, help="prefix of the output files")
+    parser.add_argument("--maxLength", type=int, default=50000, help="longest junction kept")
+    parser.add_argument("--minLength", type=int, default=50, help="shortest junction kept")
+    parser.add_argument("--minOverhang", type=int, default=5, help="least read overhang supporting a junction")
+    parser.add_argument("--drim", action="store_true", help="also write the DRIMSeq table")
+    parser.add_argument("--noMultimap", action="store_true", help="count uniquely mapped reads only (SJ.out.tab)")
+    parser.add_argument("--filter", default="gtag_only", choices=["gtag_only"], help="intron motifs kept")
+    parser.add_argument("--minUnique", type=int, default=5, help="least score for a sample to admit a junction")
+    parser.add_argument("--lowCoverageNan", action="store_true", help="NaN for cells scored below minUnique")
+    parser.add_argument("--minEntropy", type=float, default=1, help="least Shannon diversity of read offsets")
+    parser.add_argument("--device", type=int, default=0, help="CUDA device ordinal")
+
+
+def run_with(args):
+    SPLICEDICE(args.manifest, args.output_prefix, args, device=getattr(args, "device", 0))
+
+
+if __name__ == "__main__":
+    import argparse
+    cli = argparse.ArgumentParser(description="SpliceDICE quant on a B200")
+    add_parser(cli)
+    run_with(cli.parse_args())

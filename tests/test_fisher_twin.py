@@ -1,0 +1,85 @@
+"""The kernel's per-table Fisher arithmetic (splicedice_b200/csrc/sd_fisher_math.cuh) compiled
+for the host -- TEST-ONLY build under tests/cpu_twin -- against the scipy golden tables, the
+exact rational sums and the binary128 oracle.  Lets the CPU suite catch arithmetic regressions
+without a GPU; the GPU suite runs the same vectors through the real kernel."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import fisher_c
+from tests import util
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+@pytest.fixture(scope="module")
+def twin():
+    out_dir = os.path.join(HERE, "cpu_twin", "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    lib = os.path.join(out_dir, "libfisher_twin.so")
+    srcs = [os.path.join(HERE, "cpu_twin", "fisher_twin.cpp"),
+            os.path.join(ROOT, "splicedice_b200", "csrc", "sd_lgtable.cpp")]
+    deps = srcs + [os.path.join(ROOT, "splicedice_b200", "csrc", "sd_fisher_math.cuh")]
+    if not os.path.isfile(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):
+        subprocess.run(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-ffp-contract=off", "-o", lib, *srcs,
+                        "-lquadmath", "-lm"], check=True)
+    handle = ctypes.CDLL(lib)
+    i64p = ctypes.POINTER(ctypes.c_int64)
+
+    def run(tables, cap=0):
+        t = np.ascontiguousarray(tables, dtype=np.int64)
+        cols = [np.ascontiguousarray(t[:, i]) for i in range(4)]
+        out = np.empty(len(t))
+        handle.fisher_twin_batch(ctypes.c_int64(len(t)), *[c.ctypes.data_as(i64p) for c in cols],
+                                 out.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), ctypes.c_int64(cap))
+        return out
+    return run
+
+
+def _max_rel(got, want):
+    ok = want > 1e-300
+    return float((np.abs(got[ok] - want[ok]) / want[ok]).max(initial=0.0))
+
+
+def test_scipy_golden(twin):
+    g = util.load_npz("fisher_tables.npz")
+    got = twin(g["tables"])
+    assert _max_rel(got, g["p"]) < 1e-9
+    assert np.array_equal(got[g["p"] == 1.0], g["p"][g["p"] == 1.0])
+
+
+def test_exact_rational(twin):
+    g = util.load_npz("fisher_exact_small.npz")
+    np.testing.assert_allclose(twin(g["tables"]), g["p"], rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("scale,n", [(5, 50000), (60, 50000), (700, 30000), (9000, 8000), (150000, 400)])
+def test_random_vs_binary128(twin, scale, n):
+    rng = np.random.default_rng(scale)
+    t = rng.integers(0, scale, size=(n, 4))
+    t[::4, 0] *= 3
+    want = fisher_c.fisher_two_sided(t[:, 0], t[:, 1], t[:, 2], t[:, 3])
+    assert _max_rel(twin(t), want) < 1e-11
+
+
+def test_beyond_the_table_cap_uses_lgamma(twin):
+    rng = np.random.default_rng(3)
+    t = rng.integers(0, 3000, size=(5000, 4))
+    want = fisher_c.fisher_two_sided(t[:, 0], t[:, 1], t[:, 2], t[:, 3])
+    assert _max_rel(twin(t, cap=900), want) < 1e-9
+
+
+def test_mirror_ties_are_included(twin):
+    """Symmetric tables: the mirror term equals pmf(observed) exactly and must be counted."""
+    rng = np.random.default_rng(9)
+    rows = []
+    for _ in range(500):
+        a, b = (int(x) for x in rng.integers(0, 3000, 2))
+        rows.append([a, b, b, a])
+    t = np.array(rows)
+    want = fisher_c.fisher_two_sided(t[:, 0], t[:, 1], t[:, 2], t[:, 3])
+    assert _max_rel(twin(t), want) < 1e-11
