@@ -1,0 +1,126 @@
+"""Host-side logic that needs no GPU: name <-> tuple, CSR construction from the cluster files
+with the reference's two lookup semantics, Benjamini-Hochberg, file parsers on the goldens."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle_np
+from splicedice_b200 import counts_to_ps, ir_table, junctions as jn, pairwise_fisher
+
+
+def test_names_round_trip():
+    j = ("chr10", 50, 250, "-")
+    assert jn.junction_name(j) == "chr10:50-250:-" and jn.parse_name("chr10:50-250:-") == j
+    with pytest.raises(ValueError):
+        jn.parse_name("chr1:100:+")
+
+
+def test_string_ranks_follow_python_order():
+    ranks, names = jn.dense_ranks(["chr2", "chr10", "chr1", "chr10"])
+    assert names == ["chr1", "chr10", "chr2"] and ranks.tolist() == [2, 1, 0, 1]
+    t = jn.JunctionTable([("chr2", 5, 9, "-"), ("chr10", 1, 4, "+")])
+    assert t.chrom_rank.tolist() == [1, 0] and t.strand_rank.tolist() == [1, 0]      # '+' < '-'
+    with pytest.raises(ValueError):
+        jn.JunctionTable([("chr1", -1, 5, "+")])
+
+
+def test_csr_sum_semantics():
+    names = ["a", "b", "c"]
+    clusters = {"a": ["b", "b", ""], "b": [""], "c": ["a"]}
+    rp, ci = jn.csr_from_named_lists(names, clusters, "sum")
+    assert rp.tolist() == [0, 2, 2, 3] and ci.tolist() == [1, 1, 0]        # duplicates count twice
+    with pytest.raises(KeyError):
+        jn.csr_from_named_lists(names, {"a": ["zz"], "b": [], "c": []}, "sum")
+
+
+def test_csr_isin_semantics():
+    names = ["a", "b", "a", "c"]                                             # a repeated row name
+    clusters = {"a": ["b", "b", "missing"], "b": ["a"], "c": []}
+    rp, ci = jn.csr_from_named_lists(names, clusters, "isin")
+    assert rp.tolist() == [0, 1, 3, 4, 4] and ci.tolist() == [1, 0, 2, 1]    # sets; both 'a' rows selected
+    with pytest.raises(KeyError):
+        jn.csr_from_named_lists(["a", "d"], clusters, "isin")
+
+
+def test_bh_matches_oracle_and_known_values():
+    rng = np.random.default_rng(0)
+    p = rng.random(500)
+    p[::17] = p[3]                                                           # ties
+    np.testing.assert_array_equal(pairwise_fisher.fdr_bh(p), oracle_np.bh_adjust(p))
+    np.testing.assert_allclose(pairwise_fisher.fdr_bh([0.01, 0.04, 0.03, 0.005]), [0.02, 0.04, 0.04, 0.02])
+    assert pairwise_fisher.fdr_bh([]).size == 0
+
+
+def test_pair_order():
+    assert pairwise_fisher.sample_pairs(4) == [(0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3)]
+
+
+def test_parsers_on_reference_files(golden_dir):
+    exp = os.path.join(golden_dir, "survey_vector", "expected")
+    cl = counts_to_ps.get_clusters(os.path.join(exp, "ref_allClusters.tsv"))
+    assert cl["chr1:100-300:-"] == [""] and cl["chr2:50-250:+"] == ["chr2:60-200:+"]
+    header, counts = counts_to_ps.get_counts(os.path.join(exp, "ref_inclusionCounts.tsv"))
+    assert header == "cluster\ts0\ts1\ts2\n" and counts["chr1:100-300:+"].tolist() == [34.0, 32.0, 22.0]
+    pc = pairwise_fisher.getClusters(os.path.join(exp, "ref_allClusters.tsv"))
+    assert pc["chr1:100-300:-"] == [] and pc["chr1:301-600:+"] == ["chr1:300-500:+", "chr1:100-400:+"]
+    samples, events, mat = pairwise_fisher.getEventCounts(os.path.join(exp, "ref_inclusionCounts.tsv"))
+    assert samples == ["s0", "s1", "s2"] and len(events) == 9 and mat.shape == (9, 3)
+    _, ev2, m2 = pairwise_fisher.getEventCounts(os.path.join(exp, "ref_inclusionCounts.tsv"), {"chr2:60-200:+"})
+    assert ev2 == ["chr2:60-200:+"] and m2.tolist() == [[7.0, 21.0, 22.0]]
+    ic = ir_table.getClusters(os.path.join(exp, "ref_allClusters.tsv"))
+    assert ic["chr1:700-900:+"] == []
+
+
+def test_gtf_introns(tmp_path):
+    gtf = tmp_path / "a.gtf"
+    gtf.write_text(
+        "#comment\n"
+        'chr1\tx\ttranscript\t100\t900\t.\t+\t.\tgene_id "g1"; transcript_id "t1"; gene_name "G";\n'
+        'chr1\tx\texon\t100\t200\t.\t+\t.\tgene_id "g1"; transcript_id "t1";\n'
+        'chr1\tx\texon\t400\t500\t.\t+\t.\tgene_id "g1"; transcript_id "t1";\n'
+        'chr1\tx\texon\t800\t900\t.\t+\t.\tgene_id "g1"; transcript_id "t1";\n')
+    assert ir_table.getAnnotated(str(gtf)) == {"chr1:200-399:+", "chr1:500-799:+"}
+
+
+def test_sample_type_sniffing(tmp_path):
+    from splicedice_b200 import quant
+    plain = tmp_path / "a.junc.bed"
+    plain.write_text("chr1\t1\t100\tj0\t7\t+\n")
+    tagged = tmp_path / "b.bed"
+    tagged.write_text("chr1\t1\t100\te:1.20:1.30;o:9;m:GT_AG;a:?\t7\t+\n")
+    assert quant.Sample(["a", str(plain), "m", "c"]).type == "bed"
+    assert quant.Sample(["b", str(tagged), "m", "c"]).type == "splicedicebed"
+    assert quant.Sample(["c", "x.SJ.out.tab", "m", "c"]).type == "SJ"
+    assert quant.Sample(["d", "x.bam", "m", "c"]).type == "bam"
+    assert quant.Sample(["e", "x.leafcutter.junc", "m", "c"]).type == "leafcutter"
+    assert quant.Sample(["f", "x.junc", "m", "c"]).type == "unknown"
+
+
+def test_junction_filters(tmp_path):
+    """SJ.out.tab uses strict length bounds, BED inclusive ones; tagged BED filters only unannotated."""
+    import argparse
+    from splicedice_b200 import quant
+    sj = tmp_path / "s.SJ.out.tab"
+    sj.write_text("chr1\t101\t150\t1\t1\t0\t9\t0\t20\n"        # length 50: not > minLength -> out
+                  "chr1\t101\t151\t1\t1\t0\t3\t2\t20\n"        # length 51, score 3+2 -> in
+                  "chr1\t101\t400\t0\t1\t0\t9\t0\t20\n"        # undefined strand -> out
+                  "chr1\t101\t500\t2\t3\t0\t9\t0\t20\n")       # motif 3 not in gtag_only -> out
+    bed = tmp_path / "p.bed"
+    bed.write_text("chr2\t100\t150\tj\t5\t+\n"                 # length 50 inclusive -> in
+                   "chr2\t100\t149\tj\t9\t+\n"                 # too short
+                   "chr2\t100\t900\tj\t4\t-\n"                 # score < minUnique
+                   "chr2\t100\t800\tj\t9\t.\n")                # no strand
+    tag = tmp_path / "t.bed"
+    tag.write_text("chr3\t100\t900\te:0.10:0.20;o:1;m:GT_AG;a:GENE\t1\t+\n"   # annotated: no filter at all
+                   "chr3\t100\t800\te:0.10:2.00;o:9;m:GT_AG;a:?\t9\t+\n"      # low entropy
+                   "chr3\t100\t700\te:1.10:2.00;o:9;m:GT_AG;a:?\t9\t-\n")     # passes
+    man = tmp_path / "m.txt"
+    man.write_text(f"a\t{sj}\tx\ty\nb\t{bed}\tx\ty\nc\t{tag}\tx\ty\n")
+    p = argparse.ArgumentParser()
+    quant.add_parser(p)
+    args = p.parse_args(["-m", str(man), "-o", str(tmp_path / "o")])
+    job = quant.SPLICEDICE(args.manifest, args.output_prefix, args, run=False)
+    job.manifest = job.parseManifest()
+    assert job.getAllJunctions() == {("chr1", 100, 151, "+"), ("chr2", 100, 150, "+"),
+                                     ("chr3", 100, 900, "+"), ("chr3", 100, 700, "-")}
