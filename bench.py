@@ -129,6 +129,19 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(rows, samples):
+    """dram__bytes_read + dram__bytes_write of one launch from the committed ncu capture
+    (profiles/), valid only for the shape it was taken on."""
+    path = os.path.join(ROOT, "profiles", "quant_traffic.json")
+    try:
+        d = json.load(open(path))
+        if d["rows"] == rows and d["samples"] == samples:
+            return d["dram_bytes_read"] + d["dram_bytes_write"], d["source"]
+    except Exception:
+        pass
+    return None, None
+
+
 # ------------------------------------------------------------------------------------------
 # CPU baseline (oracle port; also the --impl reference arm)
 # ------------------------------------------------------------------------------------------
@@ -140,15 +153,21 @@ def cpu_quant_sample(n_rows, n_samples, seed):
     return js, counts
 
 
-def _psi_slab(args):
+_FORK_STATE = {}
+
+
+def _psi_slab(slab):
+    """One worker's share of the psi loop; inputs are inherited through fork (no pickling), only a
+    checksum travels back."""
     from oracle import ref_port
-    adjacency, index, counts, keys = args
-    sub = {k: adjacency[k] for k in keys}
-    return ref_port.psi_loop(sub, index, counts)
+    adjacency, index, counts, keys, workers = (_FORK_STATE[k] for k in ("adjacency", "index", "counts", "keys", "workers"))
+    out = ref_port.psi_rows(adjacency, index, counts, keys[slab::workers])
+    return float(np.nansum(out))
 
 
 def cpu_quant_time(js, counts, workers=1):
-    """Seconds of the reference's getClusters + row index + calculatePsi (ported loops)."""
+    """Seconds of the reference's getClusters + row index + calculatePsi (ported loops); with
+    workers > 1 the psi rows are dealt round-robin to forked processes."""
     from oracle import ref_port
     t0 = time.perf_counter()
     adjacency = ref_port.sweep_clusters(js)
@@ -157,10 +176,10 @@ def cpu_quant_time(js, counts, workers=1):
         ref_port.psi_loop(adjacency, index, counts)
     else:
         import multiprocessing as mp
-        keys = sorted(adjacency)
-        slabs = [keys[i::workers] for i in range(workers)]
+        _FORK_STATE.update(adjacency=adjacency, index=index, counts=counts, keys=sorted(adjacency), workers=workers)
         with mp.get_context("fork").Pool(workers) as pool:
-            pool.map(_psi_slab, [(adjacency, index, counts, s) for s in slabs])
+            pool.map(_psi_slab, range(workers))
+        _FORK_STATE.clear()
     return time.perf_counter() - t0
 
 
@@ -271,11 +290,11 @@ def main():
     def step():
         ops.quant_ps(counts, d_rp, d_ci, out_f32=ps, flags=args.flags)
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
     ev[0].record()
@@ -283,7 +302,6 @@ def main():
         step()
         ev[i + 1].record()
     barrier()
-    clocks = sampler.stop()
     per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
     total_ms = max_over_ranks(ev[0].elapsed_time(ev[-1]))
     cells_total = sum_over_ranks(float(cells_rank))
@@ -395,6 +413,9 @@ def main():
             del out_h
         del pout
 
+    clocks = sampler.stop()
+    clocks["window"] = "warm-up, timed steps, e2e and Fisher sections (the timed K2 region alone lasts ~10 ms)"
+
     # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -411,6 +432,7 @@ def main():
                                                 f"{args.fisher_samples * (args.fisher_samples - 1) // 2} pairs: "
                                                 f"oracle/ref_port.py pairwise_loop (scipy.stats.fisher_exact per table)"}
 
+    traffic, traffic_src = ncu_traffic(Jr, S)
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -421,7 +443,7 @@ def main():
                        "l2": "inputs+outputs 3.2 GB per pass >> 126 MB L2, no flush", "seed": SEED,
                        "cluster_build_ms": t_k1 * 1e3, "flags": args.flags},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "quant_tiled_kernel", "kernel_ms": kernel_ms,
+                         "traffic": traffic, "traffic_source": traffic_src, "kernel": "quant_wide_kernel<2, true>", "kernel_ms": kernel_ms,
                          "bytes_per_cell": 8, "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks, "fisher": fisher,
         }

@@ -66,6 +66,21 @@ def psi_loop(adjacency, index, counts_f32, low=None):
     return out
 
 
+def psi_rows(adjacency, index, counts_f32, keys):
+    """The body of ``psi_loop`` for the listed junctions only, returning just their rows
+    (row-slab fan-out of the CPU baseline over processes)."""
+    n_samples = counts_f32.shape[1]
+    out = np.zeros((len(keys), n_samples), dtype="float32")
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for k, junction in enumerate(keys):
+            inc = counts_f32[index[junction], :]
+            exc = np.zeros(n_samples)
+            for other in adjacency[junction]:
+                exc += counts_f32[index[other], :]
+            out[k, :] = inc / (inc + exc)
+    return out
+
+
 def ps_from_tables(clusters_by_name, counts_by_name):
     """Port of the arithmetic in ``counts_to_ps.writePsValues`` (counts_to_ps.py:61-68),
     returning {name: float64[S]} instead of writing the TSV."""
