@@ -77,7 +77,7 @@ __device__ __forceinline__ void stage_table(double2 *s_tab, const double2 *g_tab
 }
 
 template <class Int, int kMode>
-__global__ void __launch_bounds__(kFisherThreads, 2) fisher_pairwise_kernel(const FisherParams p)
+__global__ void __launch_bounds__(kFisherThreads, 3) fisher_pairwise_kernel(const FisherParams p)
 {
     extern __shared__ __align__(16) double2 s_tab[];
     stage_table(s_tab, p.table, p.smem_entries);

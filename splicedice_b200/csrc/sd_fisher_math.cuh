@@ -55,6 +55,15 @@ SD_HD dd dd_add(dd x, dd y)
 }
 SD_HD dd dd_sub(dd x, dd y) { return dd_add(x, dd_make(-y.hi, -y.lo)); }
 
+// (sum, err) += (h, l): error-free TwoSum of the leading words, everything else into err
+SD_HD void acc_two_sum(double &sum, double &err, double h, double l)
+{
+    const double s = sum + h;
+    const double bb = s - sum;
+    err += ((sum - (s - bb)) + (h - bb)) + l;
+    sum = s;
+}
+
 constexpr double kEps = 1e-14;                          // scipy's epsilon (:5082)
 constexpr double kLogGamma = 9.992007221626358e-15;     // log(1 + 1e-14) with 1 + 1e-14 formed in binary64
 constexpr double kTieWindow = 1.0000000000000051e-14;   // -log(1 - 1e-14)
@@ -189,15 +198,24 @@ SD_HD double two_sided(const Table &tab, Int a, Int b, Int c, Int d)
         }
     }
 
-    // log pmf(a) in double-double
-    dd lp = dd_add(tab.get(n1), tab.get(n2));
-    lp = dd_add(lp, tab.get(n));
-    lp = dd_add(lp, tab.get(N - n));
-    lp = dd_sub(lp, tab.get(N));
-    lp = dd_sub(lp, tab.get(a));
-    lp = dd_sub(lp, tab.get(b));
-    lp = dd_sub(lp, tab.get(c));
-    lp = dd_sub(lp, tab.get(d));
+    // log pmf(a): compensated sum of the nine table entries (TwoSum on the hi words, the
+    // rounding errors and lo words accumulated separately)
+    double lp_hi, lp_lo;
+    {
+        const dd t0 = tab.get(n1), t1 = tab.get(n2), t2 = tab.get(n), t3 = tab.get(N - n), t4 = tab.get(N);
+        const dd t5 = tab.get(a), t6 = tab.get(b), t7 = tab.get(c), t8 = tab.get(d);
+        double sum = t0.hi, err = t0.lo;
+        acc_two_sum(sum, err, t1.hi, t1.lo);
+        acc_two_sum(sum, err, t2.hi, t2.lo);
+        acc_two_sum(sum, err, t3.hi, t3.lo);
+        acc_two_sum(sum, err, -t4.hi, -t4.lo);
+        acc_two_sum(sum, err, -t5.hi, -t5.lo);
+        acc_two_sum(sum, err, -t6.hi, -t6.lo);
+        acc_two_sum(sum, err, -t7.hi, -t7.lo);
+        acc_two_sum(sum, err, -t8.hi, -t8.lo);
+        lp_hi = sum + err;
+        lp_lo = err - (lp_hi - sum);
+    }
 
     // smallest g in (mode, hi] with admitted(g): start from the mirror image of a, gallop, bisect
     Int lo_x = mode, hi_x = hi + 1;
@@ -240,8 +258,8 @@ SD_HD double two_sided(const Table &tab, Int a, Int b, Int c, Int d)
         if (g <= hi)
             rel = fma(tg, tail_sum((double)(n1 - g), (double)(n - g), (double)g, (double)(n2 - n + g)), rel);
     }
-    double pexact = exp(lp.hi);
-    pexact = fma(pexact, lp.lo, pexact);
+    double pexact = exp(lp_hi);
+    pexact = fma(pexact, lp_lo, pexact);
     const double p = pexact * rel;
     return p > 1.0 ? 1.0 : p;
 }

@@ -28,6 +28,7 @@ struct QuantParams {
     int32_t lpr_log2;        // log2(lanes per row); C = 4 << lpr_log2 columns per slab
     int32_t n_slabs;
     int32_t vec_stores;      // outputs are 16-byte aligned with ld % 4 == 0
+    int32_t ir_vec;          // median / ir are 16-byte aligned with even ld
 };
 
 // Chooses tiled / gather kernel and launches it on `stream` (flags: SD_QUANT_*).

@@ -53,5 +53,60 @@ def main():
         print(f"fisher {J}x{len(pa)}: {ms:.3f} ms/launch, {J * len(pa) / (ms * 1e-3):.3e} tests/s")
 
 
+
+
+def misc():
+    """K1 timing, narrow-matrix quant (configs[0] shape), IR (configs[4]) -- CUDA events."""
+    import time
+    dev = torch.device("cuda", 0)
+    for J in (50_000, 400_000, 1_000_000):
+        arrays = synth.junction_arrays(J, 3)[:4]
+        d = [torch.from_numpy(a).to(dev) for a in arrays]
+        ops.cluster_build(*d)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            cl = ops.cluster_build(*d)
+        torch.cuda.synchronize()
+        print(f"cluster_build J={J}: {(time.perf_counter() - t0) / 5 * 1e3:.2f} ms/call (nnz {cl['nnz']}, {cl['n_comp']} components)")
+    for J, S in ((50_000, 8), (400_000, 64), (400_000, 1000)):
+        cl = ops.cluster_build(*synth.junction_arrays(J, 3)[:4])
+        counts = ops.synth_counts(1, 0, J, S, device=dev)
+        ps = torch.empty((J, S), dtype=torch.float32, device=dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for i in range(12):
+            if i == 2:
+                e0.record()
+            ops.quant_ps(counts, cl["row_ptr"], cl["col_idx"], out_f32=ps)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        print(f"quant {J}x{S}: {ms * 1e3:.1f} us/launch, {J * S * 8 / ms / 1e6:.0f} GB/s algorithmic")
+        if S == 1000:
+            med = torch.rand((J, S), dtype=torch.float64, device=dev).mul_(10).floor_()
+            for i in range(6):
+                if i == 1:
+                    e0.record()
+                ir = ops.ir_ratio(med, counts, cl["row_ptr"], cl["col_idx"])
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 5
+            print(f"ir_ratio {J}x{S}: {ms:.3f} ms/launch (incl. output allocation), {J * S * 20 / ms / 1e6:.0f} GB/s algorithmic (20 B/cell)")
+            ps64 = torch.empty((J, S), dtype=torch.float64, device=dev)
+            for i in range(6):
+                if i == 1:
+                    e0.record()
+                ops.quant_ps(counts, cl["row_ptr"], cl["col_idx"], want_f32=False, out_f64=ps64)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 5
+            print(f"quant f64 PS {J}x{S}: {ms:.3f} ms/launch, {J * S * 12 / ms / 1e6:.0f} GB/s algorithmic (12 B/cell)")
+
+
+if len(sys.argv) > 1 and sys.argv[1] == "misc":
+    misc()
+    sys.exit(0)
+
+
 if __name__ == "__main__":
     main()
