@@ -173,6 +173,21 @@ int sd_ir_ratio(int64_t n_junctions, int32_t n_samples,
                 int64_t row_begin, int64_t row_end, void *stream);
 int sd_rsd5(int64_t n, const double *cov5, double *rsd_out, void *stream);
 
+/* ---- host-side text output (no CUDA) ---------------------------------------------------
+ * Replaces the per-cell f-strings of the reference's writers: SPLICEDICE.writeInclusions /
+ * writeAllpsi (SPLICEDICE.py:332-353, f'{x:.0f}' / f'{x:.3f}') and counts_to_ps.writePsValues
+ * (counts_to_ps.py:69, f"{x:0.3f}").  Formats `rows` rows of a HOST matrix as
+ * "name<TAB>v<TAB>...<TAB>v\n" (names == NULL: values only), byte-identical to the python
+ * formatting (exact round-half-even; "nan" for any NaN), on `n_threads` host threads (<= 0: all).
+ * kind 0: float32 as %.3f, 1: float64 as %.3f, 2: int32 as a decimal integer.
+ * names / name_off[rows + 1]: concatenated row names and their offsets.
+ * *written receives the byte count; SD_ERR_WORKSPACE (with *written = bytes needed) if cap is
+ * too small.
+ */
+int sd_host_format_rows(int kind, const void *matrix, int64_t rows, int32_t cols, int64_t ld,
+                        const char *names, const int64_t *name_off, char *out, size_t cap,
+                        size_t *written, int n_threads);
+
 /* ---- synthetic inputs + probes (bench / tests) --------------------------------------
  * sd_synth_counts: the counter-based generator of splicedice_b200/synth.py:counts_host,
  * bit for bit.  out[r - row0, c] for r in [row0, row0 + n_rows), c < n_cols.

@@ -93,11 +93,9 @@ def ps_matrix(clusters, counts, device=0):
 
 
 def writePsValues(clusters, header, counts, output_prefix, device=0):
+    from . import textio
     names, ps = ps_matrix(clusters, counts, device)
-    with open(f"{output_prefix}_allPS.tsv", "w") as out:
-        out.write(header)
-        for name, row in zip(names, ps.tolist()):
-            out.write(name + "\t" + "\t".join(f"{x:0.3f}" for x in row) + "\n")
+    textio.write_matrix(f"{output_prefix}_allPS.tsv", header, names, np.ascontiguousarray(ps, dtype=np.float64))
 
 
 def writeClusters(clusters, output_prefix):

@@ -165,15 +165,32 @@ struct Problem {
     }
 };
 
+// Everything about a table except its two tail sums.  `known`: the p-value is already decided
+// (zero margin, observed == mode, tie with the mode) and sits in `pexact`.  Otherwise
+//   p = pexact * (S(near tail) + tg * S(far tail)),
+// each tail described by its four starting cells (p, q shrink; u, v grow); `far[0] < 0` when the
+// far side contributes nothing.
+template <class Int>
+struct Plan {
+    bool known;
+    double pexact, tg;
+    Int near[4], far[4];
+    Int total;              // N, decides which tail-sum routine is exact
+};
+
 template <class Int, class Table>
-SD_HD double two_sided(const Table &tab, Int a, Int b, Int c, Int d)
+SD_HD Plan<Int> make_plan(const Table &tab, Int a, Int b, Int c, Int d)
 {
+    Plan<Int> pl;
+    pl.known = true; pl.pexact = 1.0; pl.tg = 0.0; pl.total = 0;
+    pl.near[0] = pl.near[1] = pl.near[2] = pl.near[3] = 0;
+    pl.far[0] = -1; pl.far[1] = pl.far[2] = pl.far[3] = 0;
     Int n1 = a + b, n2 = c + d, n = a + c;
-    if (n1 == 0 || n2 == 0 || n == 0 || b + d == 0) return 1.0;
+    if (n1 == 0 || n2 == 0 || n == 0 || b + d == 0) return pl;
     const Int N = n1 + n2;
     // numpy: int64 product, float64 divide, int() truncation
     Int mode = (Int)((double)((int64_t)(n + 1) * (int64_t)(n1 + 1)) / (double)((int64_t)N + 2));
-    if (a == mode) return 1.0;
+    if (a == mode) return pl;
     // Observed count above the mode: swap the columns.  x -> n1 - x maps the distribution onto
     // hypergeom(N, n1, N - n) with identical pmf values, so from here on a < mode and the far
     // side is the upper one.  (The reflected mode is only used as a point whose pmf exceeds
@@ -194,7 +211,7 @@ SD_HD double two_sided(const Table &tab, Int a, Int b, Int c, Int d)
         const double fm = pr.f_fast(mode);
         if (fabs(fm) <= pr.tol + kTieWindow) {
             const dd fe = pr.f_exact(mode);
-            if (fabs(fe.hi + fe.lo) <= kTieWindow) return 1.0;
+            if (fabs(fe.hi + fe.lo) <= kTieWindow) return pl;
         }
     }
 
@@ -242,26 +259,41 @@ SD_HD double two_sided(const Table &tab, Int a, Int b, Int c, Int d)
         }
     }
     const Int g = hi_x;
-    double tg = 0.0;
+    pl.known = false;
+    pl.total = N;
+    pl.near[0] = a; pl.near[1] = d; pl.near[2] = b; pl.near[3] = c;                  // a, a-1, ...
     if (g <= hi) {
         const dd fg = pr.f_exact(g);
-        tg = exp(fg.hi);
-        tg = fma(tg, fg.lo, tg);
-    }
-    double rel;
-    if ((int64_t)N < (int64_t(1) << 26)) {
-        rel = tail_fast((double)a, (double)d, (double)b, (double)c);              // a, a-1, ...
-        if (g <= hi)
-            rel = fma(tg, tail_fast((double)(n1 - g), (double)(n - g), (double)g, (double)(n2 - n + g)), rel);
-    } else {
-        rel = tail_sum((double)a, (double)d, (double)b, (double)c);
-        if (g <= hi)
-            rel = fma(tg, tail_sum((double)(n1 - g), (double)(n - g), (double)g, (double)(n2 - n + g)), rel);
+        double tg = exp(fg.hi);
+        pl.tg = fma(tg, fg.lo, tg);
+        pl.far[0] = n1 - g; pl.far[1] = n - g; pl.far[2] = g; pl.far[3] = n2 - n + g;
     }
     double pexact = exp(lp_hi);
-    pexact = fma(pexact, lp_lo, pexact);
-    const double p = pexact * rel;
+    pl.pexact = fma(pexact, lp_lo, pexact);
+    return pl;
+}
+
+SD_HD double finish(double pexact, double tg, double s_near, double s_far)
+{
+    const double p = pexact * fma(tg, s_far, s_near);
     return p > 1.0 ? 1.0 : p;
+}
+
+// tail sum of one descriptor; exact second-difference recurrences need every product < 2^52
+template <class Int>
+SD_HD double tail_of(const Int (&t)[4], Int total)
+{
+    if (t[0] < 0) return 0.0;
+    if ((int64_t)total < (int64_t(1) << 26)) return tail_fast((double)t[0], (double)t[1], (double)t[2], (double)t[3]);
+    return tail_sum((double)t[0], (double)t[1], (double)t[2], (double)t[3]);
+}
+
+template <class Int, class Table>
+SD_HD double two_sided(const Table &tab, Int a, Int b, Int c, Int d)
+{
+    const Plan<Int> pl = make_plan<Int>(tab, a, b, c, d);
+    if (pl.known) return pl.pexact;
+    return finish(pl.pexact, pl.tg, tail_of(pl.near, pl.total), tail_of(pl.far, pl.total));
 }
 
 // hypergeometric support size of a table (0 for a zero-margin table): the work unit of the

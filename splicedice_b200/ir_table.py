@@ -171,13 +171,12 @@ def calculateIR(samples, coverageDirectory, counts, clusters, annotated, args, d
 
 
 def _write(path, header, samples, junctions, table):
-    rows = table._row
+    from . import textio
+    ordered = sorted(junctions)
+    rows = [table._row[name] for name in ordered]
     cols = [table._col[s] for s in samples]
-    with open(path, "w") as out:
-        out.write(header)
-        for name in sorted(junctions):
-            vals = table.values[rows[name], cols].tolist()
-            out.write(name + "\t" + "\t".join(f"{v:0.03f}" for v in vals) + "\n")
+    block = np.ascontiguousarray(table.values[np.ix_(rows, cols)], dtype=np.float64) if rows else np.zeros((0, len(cols)))
+    textio.write_matrix(path, header, ordered, block)
 
 
 def writeIRtable(samples, outputPrefix, junctions, IR):

@@ -262,18 +262,18 @@ class SPLICEDICE:
             for r, name in enumerate(names):
                 out.write(name + "\t" + ",".join(names[c] for c in ci[rp[r]:rp[r + 1]]) + "\n")
 
-    def _write_matrix(self, path, matrix, fmt):
+    def _write_matrix(self, path, matrix):
+        """cluster<TAB>samples header, then name<TAB>values rows through the native formatter
+        (byte-identical to the reference's f'{x:.0f}' / f'{x:.3f}' per cell)."""
+        from . import textio
         names = [jn.junction_name(j) for j in self._rows]
-        with open(path, "w") as out:
-            out.write("cluster\t" + "\t".join(s.name for s in self.manifest) + "\n")
-            for name, row in zip(names, matrix.tolist()):
-                out.write(name + "\t" + "\t".join(fmt(x) for x in row) + "\n")
+        textio.write_matrix(path, "cluster\t" + "\t".join(s.name for s in self.manifest) + "\n", names, matrix)
 
     def writeInclusions(self):
-        self._write_matrix(f"{self.outputPrefix}_inclusionCounts.tsv", self.counts, lambda x: f"{x:.0f}")
+        self._write_matrix(f"{self.outputPrefix}_inclusionCounts.tsv", np.ascontiguousarray(self.counts, dtype=np.int32))
 
     def writeAllpsi(self):
-        self._write_matrix(f"{self.outputPrefix}_allPS.tsv", self.psi, lambda x: f"{x:.3f}")
+        self._write_matrix(f"{self.outputPrefix}_allPS.tsv", np.ascontiguousarray(self.psi, dtype=np.float32))
 
     def writeDrimLine(self, i, junction, other, file):
         # the reference prints its float32 counts with astype(str): "34.0"

@@ -1,0 +1,82 @@
+"""The BASELINE.json shapes at full size, checked through properties that do not need the whole
+matrix on the host: rows sampled from the device result are re-made on the CPU with the
+counter-based generator (splicedice_b200.synth) and compared bit for bit with the oracle;
+ranges / NaN rules / symmetry are checked on the whole device result."""
+import numpy as np
+import pytest
+
+from oracle import fisher_c, oracle_np
+from tests import util
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def _rows_check(ops, synth, seed, J, S, row0, csr, ps, n_rows=160):
+    rp, ci = csr
+    rng = np.random.default_rng(seed)
+    rows = np.sort(rng.choice(J, size=n_rows, replace=False))
+    need = sorted(set(rows.tolist()) | {int(c) for r in rows for c in ci[rp[r]:rp[r + 1]]})
+    host = synth.counts_host(seed, 0, len(need), S, rows=[row0 + r for r in need], ld_cols=S).astype(np.int64)
+    at = {r: k for k, r in enumerate(need)}
+    got = ps[torch.from_numpy(rows).to(ps.device)].cpu().numpy()
+    for k, r in enumerate(rows):
+        inc = host[at[int(r)]]
+        exc = host[[at[int(c)] for c in ci[rp[r]:rp[r + 1]]]].sum(axis=0) if rp[r + 1] > rp[r] else np.zeros(S, np.int64)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            want = (inc.astype(np.float32) / (inc.astype(np.float32) + exc.astype(np.float64))).astype(np.float32)
+        np.testing.assert_array_equal(util.bits32(got[k]), util.bits32(want), err_msg=f"row {r}")
+
+
+@pytest.mark.parametrize("J,S,label", [(400_000, 1000, "configs[1] GTEx-scale"),
+                                       (125_000, 10_000, "configs[3] TCGA-scale, one of 8 shards")])
+def test_quant_ps_full_size(J, S, label):
+    from splicedice_b200 import ops, synth
+    ops.require_cuda()
+    dev = torch.device("cuda", 0)
+    cl = ops.cluster_build(*synth.junction_arrays(J, 77)[:4])
+    csr = (cl["row_ptr"].cpu().numpy(), cl["col_idx"].cpu().numpy())
+    counts = ops.synth_counts(5, 0, J, S, device=dev)
+    ps = ops.quant_ps(counts, cl["row_ptr"], cl["col_idx"])["ps_f32"]
+    torch.cuda.synchronize()
+    _rows_check(ops, synth, 5, J, S, 0, csr, ps)
+    # whole-matrix properties: 0 <= PS <= 1 or NaN; NaN exactly where the junction and all of its
+    # neighbours are zero; a junction without neighbours has PS 1 wherever it is covered
+    finite = ~torch.isnan(ps)
+    assert bool(((ps[finite] >= 0) & (ps[finite] <= 1)).all())
+    lonely = torch.from_numpy(np.flatnonzero(np.diff(csr[0]) == 0)).to(dev)
+    sub_c, sub_p = counts[lonely], ps[lonely]
+    assert bool(torch.isnan(sub_p[sub_c == 0]).all()) and bool((sub_p[sub_c > 0] == 1).all())
+    assert bool((ps[counts == 0][~torch.isnan(ps[counts == 0])] == 0).all())
+    # idempotence / determinism: a second launch writes the same bits
+    again = ops.quant_ps(counts, cl["row_ptr"], cl["col_idx"])["ps_f32"]
+    assert torch.equal(ps.view(torch.int32), again.view(torch.int32))
+
+
+def test_pairwise_fisher_full_size():
+    """configs[2]: 64 samples (2,016 pairs) x 200,000 junctions = 4.03e8 tests."""
+    from splicedice_b200 import ops, synth
+    ops.require_cuda()
+    dev = torch.device("cuda", 0)
+    J, S = 200_000, 64
+    cl = ops.cluster_build(*synth.junction_arrays(J, 78)[:4])
+    inc = ops.synth_counts(8, 0, J, S, device=dev) + ops.synth_counts(9, 0, J, S, device=dev)
+    exc = ops.quant_ps(inc, cl["row_ptr"], cl["col_idx"], want_f32=False, want_exc=True)["exc"]
+    pa, pb = ops.all_pairs(S)
+    p = ops.fisher_pairwise(inc, exc, pa, pb)
+    torch.cuda.synchronize()
+    assert p.shape == (J, 2016)
+    assert not bool(torch.isnan(p).any()) and bool(((p >= 0) & (p <= 1)).all())    # p < 1e-308 underflows to 0, as scipy
+    # zero-margin rows (no neighbours, so exc = 0) are exactly 1
+    lonely = torch.from_numpy(np.flatnonzero(np.diff(cl["row_ptr"].cpu().numpy()) == 0)).to(dev)
+    assert bool((p[lonely] == 1).all())
+    # symmetry: swapping the two samples of every pair leaves p unchanged
+    rows = torch.from_numpy(np.sort(np.random.default_rng(1).choice(J, 4000, replace=False))).to(dev)
+    swapped = ops.fisher_pairwise(inc[rows].contiguous(), exc[rows].contiguous(), pb, pa)
+    torch.testing.assert_close(swapped, p[rows], rtol=1e-12, atol=0)
+    # sampled rows against the binary128 oracle
+    sel = rows[:150]
+    want = fisher_c.pairwise(inc[sel].cpu().numpy(), exc[sel].cpu().numpy(), pa, pb)
+    got = p[sel].cpu().numpy()
+    ok = want > 1e-300
+    assert (np.abs(got[ok] - want[ok]) / want[ok]).max() < 1e-11

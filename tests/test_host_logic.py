@@ -124,3 +124,28 @@ def test_junction_filters(tmp_path):
     job.manifest = job.parseManifest()
     assert job.getAllJunctions() == {("chr1", 100, 151, "+"), ("chr2", 100, 150, "+"),
                                      ("chr3", 100, 900, "+"), ("chr3", 100, 700, "-")}
+
+
+def test_native_row_formatter_is_byte_identical_to_python():
+    """sd_host_format_rows against the reference's per-cell f-strings (SPLICEDICE.py:340,353;
+    counts_to_ps.py:69): exact round-half-even on the binary value, 'nan' for any NaN."""
+    from splicedice_b200 import textio
+    rng = np.random.default_rng(0)
+    x = rng.random((700, 130)).astype(np.float32)
+    x[rng.random(x.shape) < 0.05] = np.nan
+    x[0, :9] = [0.0625, 0.1875, 0.0005, 0.0015, 0.9995, 1.0, 0.0, -0.0, np.float32(-np.nan)]
+    names = [f"chr{i % 22 + 1}:{i}-{i + 100}:{'+-'[i % 2]}" for i in range(700)]
+    want = "".join(n + "\t" + "\t".join(f"{v:.3f}" for v in row) + "\n" for n, row in zip(names, x.tolist()))
+    assert textio.format_rows(x, names) == want.encode()
+    assert textio.format_rows(x, names, threads=1) == want.encode()
+    y = np.concatenate([rng.random(60000), rng.integers(0, 10 ** 7, 60000) / 8000.0,
+                        np.array([0.0005, 0.0015, 0.0025, 1e15, 1e17, -3.14159, np.inf, -np.inf, np.nan, 5e-324, 4.0e12]),
+                        rng.standard_normal(30000) * 1e6])
+    y = np.concatenate([y, np.zeros((-len(y)) % 40)]).reshape(-1, 40)
+    want = "".join("\t".join(f"{v:0.3f}" for v in row) + "\n" for row in y.tolist())
+    assert textio.format_rows(y) == want.encode()
+    z = rng.integers(0, 2 ** 31 - 1, size=(300, 17)).astype(np.int32)
+    z[0, :2] = [0, 2 ** 31 - 1]
+    want = "".join("\t".join(f"{float(v):.0f}" for v in row) + "\n" for row in z.tolist())
+    assert textio.format_rows(z) == want.encode()
+    assert textio.format_rows(np.zeros((0, 5), dtype=np.float32), []) == b""
