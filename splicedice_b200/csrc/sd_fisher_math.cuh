@@ -273,27 +273,23 @@ SD_HD Plan<Int> make_plan(const Table &tab, Int a, Int b, Int c, Int d)
     return pl;
 }
 
-SD_HD double finish(double pexact, double tg, double s_near, double s_far)
-{
-    const double p = pexact * fma(tg, s_far, s_near);
-    return p > 1.0 ? 1.0 : p;
-}
-
-// tail sum of one descriptor; exact second-difference recurrences need every product < 2^52
-template <class Int>
-SD_HD double tail_of(const Int (&t)[4], Int total)
-{
-    if (t[0] < 0) return 0.0;
-    if ((int64_t)total < (int64_t(1) << 26)) return tail_fast((double)t[0], (double)t[1], (double)t[2], (double)t[3]);
-    return tail_sum((double)t[0], (double)t[1], (double)t[2], (double)t[3]);
-}
-
 template <class Int, class Table>
 SD_HD double two_sided(const Table &tab, Int a, Int b, Int c, Int d)
 {
     const Plan<Int> pl = make_plan<Int>(tab, a, b, c, d);
     if (pl.known) return pl.pexact;
-    return finish(pl.pexact, pl.tg, tail_of(pl.near, pl.total), tail_of(pl.far, pl.total));
+    double rel;
+    if ((int64_t)pl.total < (int64_t(1) << 26)) {
+        rel = tail_fast((double)pl.near[0], (double)pl.near[1], (double)pl.near[2], (double)pl.near[3]);
+        if (pl.far[0] >= 0)
+            rel = fma(pl.tg, tail_fast((double)pl.far[0], (double)pl.far[1], (double)pl.far[2], (double)pl.far[3]), rel);
+    } else {
+        rel = tail_sum((double)pl.near[0], (double)pl.near[1], (double)pl.near[2], (double)pl.near[3]);
+        if (pl.far[0] >= 0)
+            rel = fma(pl.tg, tail_sum((double)pl.far[0], (double)pl.far[1], (double)pl.far[2], (double)pl.far[3]), rel);
+    }
+    const double p = pl.pexact * rel;
+    return p > 1.0 ? 1.0 : p;
 }
 
 // hypergeometric support size of a table (0 for a zero-margin table): the work unit of the
