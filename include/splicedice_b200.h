@@ -179,7 +179,8 @@ int sd_rsd5(int64_t n, const double *cov5, double *rsd_out, void *stream);
  * (counts_to_ps.py:69, f"{x:0.3f}").  Formats `rows` rows of a HOST matrix as
  * "name<TAB>v<TAB>...<TAB>v\n" (names == NULL: values only), byte-identical to the python
  * formatting (exact round-half-even; "nan" for any NaN), on `n_threads` host threads (<= 0: all).
- * kind 0: float32 as %.3f, 1: float64 as %.3f, 2: int32 as a decimal integer.
+ * kind 0: float32 as %.3f, 1: float64 as %.3f, 2: int32 as a decimal integer, 3: float64 as
+ * python's str()/repr() (shortest round-trip digits; pairwise_fisher.py:200 writes str(p)).
  * names / name_off[rows + 1]: concatenated row names and their offsets.
  * *written receives the byte count; SD_ERR_WORKSPACE (with *written = bytes needed) if cap is
  * too small.
@@ -187,6 +188,35 @@ int sd_rsd5(int64_t n, const double *cov5, double *rsd_out, void *stream);
 int sd_host_format_rows(int kind, const void *matrix, int64_t rows, int32_t cols, int64_t ld,
                         const char *names, const int64_t *name_off, char *out, size_t cap,
                         size_t *written, int n_threads);
+
+/* ---- host-side sample-file ingest for quant (no CUDA) ------------------------------------
+ * Replaces the per-line python passes SPLICEDICE.getAllJunctions (SPLICEDICE.py:147-228) and
+ * SPLICEDICE.getJunctionCounts (SPLICEDICE.py:257-295): memory-mapped files, several threads,
+ * hash-table union / lookup, the reference's admission rules per file type.
+ * File types: 0 = STAR SJ.out.tab, 1 = bam_to_junc_bed BED (tagged name field), 2 = plain BED or
+ * leafcutter; any other value = opened and ignored (.bam / unknown suffix).
+ * A malformed line fails the call with SD_ERR_INVALID and "path:line: reason".
+ */
+typedef struct sd_quant_filter {
+    int32_t max_length, min_length, min_overhang, min_unique;   /* --maxLength --minLength --minOverhang --minUnique */
+    int32_t no_multimap, low_coverage_nan;                      /* --noMultimap --lowCoverageNan */
+    uint32_t motif_mask;                                        /* bit m: STAR motif code m admitted (--filter) */
+    uint32_t reserved;
+    double min_entropy;                                         /* --minEntropy */
+} sd_quant_filter;
+void *sd_ingest_create(void);
+void sd_ingest_destroy(void *handle);
+int sd_ingest_collect(void *handle, int32_t n_files, const char *const *paths, const int32_t *types,
+                      const sd_quant_filter *filter, int32_t n_threads);
+int64_t sd_ingest_junction_count(void *handle);
+int32_t sd_ingest_chrom_count(void *handle);
+const char *sd_ingest_chrom_name(void *handle, int32_t id);
+int sd_ingest_export(void *handle, int32_t *chrom_id, int32_t *left, int32_t *right, int8_t *strand);
+int sd_ingest_index(void *handle, int64_t n, const char *const *chrom_names, const int32_t *chrom_of,
+                    const int32_t *left, const int32_t *right, const int8_t *strand, const int32_t *row);
+int sd_ingest_counts(void *handle, int32_t n_files, const char *const *paths, const int32_t *types,
+                     const int32_t *samples, const sd_quant_filter *filter, int32_t *counts,
+                     int64_t ld_counts, uint8_t *low_mask, int64_t ld_mask, int32_t n_threads);
 
 /* ---- synthetic inputs + probes (bench / tests) --------------------------------------
  * sd_synth_counts: the counter-based generator of splicedice_b200/synth.py:counts_host,

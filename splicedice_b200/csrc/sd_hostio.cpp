@@ -16,6 +16,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <charconv>
 #include <string>
 #include <thread>
 #include <vector>
@@ -66,11 +67,58 @@ inline void put_value_f(std::string &s, double v)
     s.append(buf, (size_t)n);
 }
 
+// python's repr(float) / str(numpy.float64): shortest digits that round-trip, fixed notation when
+// the decimal exponent is in [-4, 16), otherwise d.ddde[+-]XX with at least two exponent digits
+inline void put_repr(std::string &s, double v)
+{
+    if (isnan(v)) { s += "nan"; return; }
+    if (isinf(v)) { s += v < 0 ? "-inf" : "inf"; return; }
+    if (v == 0.0) { s += signbit(v) ? "-0.0" : "0.0"; return; }
+    char buf[64];
+    auto res = std::to_chars(buf, buf + sizeof buf, v, std::chars_format::scientific);   // d[.ddd]e[+-]XX, shortest
+    *res.ptr = 0;
+    const char *p = buf, *end = res.ptr;
+    if (*p == '-') { s.push_back('-'); ++p; }
+    const char *e = p;
+    while (e < end && *e != 'e') ++e;
+    char digits[40];
+    int nd = 0;
+    for (const char *q = p; q < e; ++q)
+        if (*q != '.') digits[nd++] = *q;
+    const int exp10 = atoi(e + 1);
+    if (exp10 >= -4 && exp10 < 16) {
+        if (exp10 < 0) {
+            s += "0.";
+            s.append((size_t)(-exp10 - 1), '0');
+            s.append(digits, (size_t)nd);
+        } else {
+            const int int_digits = exp10 + 1;
+            if (nd <= int_digits) {
+                s.append(digits, (size_t)nd);
+                s.append((size_t)(int_digits - nd), '0');
+                s += ".0";
+            } else {
+                s.append(digits, (size_t)int_digits);
+                s.push_back('.');
+                s.append(digits + int_digits, (size_t)(nd - int_digits));
+            }
+        }
+    } else {
+        s.push_back(digits[0]);
+        if (nd > 1) { s.push_back('.'); s.append(digits + 1, (size_t)(nd - 1)); }
+        s.push_back('e');
+        s.push_back(exp10 < 0 ? '-' : '+');
+        const int ae = exp10 < 0 ? -exp10 : exp10;
+        if (ae < 10) s.push_back('0');
+        put_uint(s, (uint64_t)ae);
+    }
+}
+
 template <class Get>
 void format_range(int64_t r0, int64_t r1, int32_t cols, const char *names, const int64_t *name_off, Get get,
                   std::string *out)
 {
-    out->reserve((size_t)(r1 - r0) * ((size_t)cols * 6 + 32));
+    out->reserve((size_t)(r1 - r0) * ((size_t)cols * 8 + 32));
     for (int64_t r = r0; r < r1; ++r) {
         if (names) out->append(names + name_off[r], (size_t)(name_off[r + 1] - name_off[r]));
         for (int32_t c = 0; c < cols; ++c) {
@@ -87,7 +135,8 @@ extern "C" int sd_host_format_rows(int kind, const void *matrix, int64_t rows, i
                                    const char *names, const int64_t *name_off, char *out, size_t cap,
                                    size_t *written, int n_threads)
 {
-    SD_REQUIRE(kind >= 0 && kind <= 2, "sd_host_format_rows: kind must be 0 (f32 %%.3f), 1 (f64 %%.3f) or 2 (i32)");
+    SD_REQUIRE(kind >= 0 && kind <= 3,
+               "sd_host_format_rows: kind must be 0 (f32 %%.3f), 1 (f64 %%.3f), 2 (i32) or 3 (f64 repr)");
     SD_REQUIRE(rows >= 0 && cols >= 0 && ld >= cols && written, "sd_host_format_rows: bad shape");
     SD_REQUIRE((rows == 0 || cols == 0 || matrix) && (!names || name_off), "sd_host_format_rows: null pointer");
     if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
@@ -103,6 +152,10 @@ extern "C" int sd_host_format_rows(int kind, const void *matrix, int64_t rows, i
             const double *m = static_cast<const double *>(matrix);
             format_range(r0, r1, cols, names, name_off,
                          [m, ld](std::string &s, int64_t r, int32_t c) { put_value_f(s, m[r * ld + c]); }, &parts[t]);
+        } else if (kind == 3) {
+            const double *m = static_cast<const double *>(matrix);
+            format_range(r0, r1, cols, names, name_off,
+                         [m, ld](std::string &s, int64_t r, int32_t c) { put_repr(s, m[r * ld + c]); }, &parts[t]);
         } else {
             const int32_t *m = static_cast<const int32_t *>(matrix);
             format_range(r0, r1, cols, names, name_off,

@@ -23,6 +23,13 @@ class NativeLibraryError(RuntimeError):
     pass
 
 
+class QuantFilter(ctypes.Structure):
+    """sd_quant_filter of include/splicedice_b200.h"""
+    _fields_ = [("max_length", c_int32), ("min_length", c_int32), ("min_overhang", c_int32), ("min_unique", c_int32),
+                ("no_multimap", c_int32), ("low_coverage_nan", c_int32), ("motif_mask", c_uint32),
+                ("reserved", c_uint32), ("min_entropy", c_double)]
+
+
 class NativeCallError(RuntimeError):
     def __init__(self, fn, code, msg):
         super().__init__(f"{fn} failed (code {code}): {msg}")
@@ -51,6 +58,15 @@ _SIGNATURES = {
     "sd_ir_ratio": (c_int, [c_int64, c_int32, _P, c_int64, _P, c_int64, _P, _P, _P, c_int64,
                             c_int64, c_int64, _P]),
     "sd_rsd5": (c_int, [c_int64, _P, _P, _P]),
+    "sd_ingest_create": (c_void_p, []),
+    "sd_ingest_destroy": (None, [_P]),
+    "sd_ingest_collect": (c_int, [_P, c_int32, _P, _P, _P, c_int32]),
+    "sd_ingest_junction_count": (c_int64, [_P]),
+    "sd_ingest_chrom_count": (c_int32, [_P]),
+    "sd_ingest_chrom_name": (c_char_p, [_P, c_int32]),
+    "sd_ingest_export": (c_int, [_P, _P, _P, _P, _P]),
+    "sd_ingest_index": (c_int, [_P, c_int64, _P, _P, _P, _P, _P, _P]),
+    "sd_ingest_counts": (c_int, [_P, c_int32, _P, _P, _P, _P, _P, c_int64, _P, c_int64, c_int32]),
     "sd_host_format_rows": (c_int, [c_int, _P, c_int64, c_int32, c_int64, _P, _P, _P, c_size_t,
                                     POINTER(c_size_t), c_int]),
     "sd_synth_counts": (c_int, [c_uint64, c_int64, c_int64, c_int32, c_int64, c_uint32, _P, c_int64, _P]),

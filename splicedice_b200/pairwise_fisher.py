@@ -120,10 +120,9 @@ def run_with(args):
     elif args.multiple_test_correction == "pairwise":
         for k in range(parray.shape[1]):
             parray[:, k] = fdr_bh(parray[:, k])
-    with open(args.output, "w") as out:
-        out.write("clusterID\t" + "\t".join(columns) + "\n")
-        for name, row in zip(events, parray):
-            out.write(name + "\t" + "\t".join(str(p) for p in row) + "\n")
+    from . import textio
+    textio.write_matrix(args.output, "clusterID\t" + "\t".join(columns) + "\n", events,
+                        np.ascontiguousarray(parray, dtype=np.float64), repr_floats=True)
 
 
 if __name__ == "__main__":

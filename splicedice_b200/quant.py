@@ -50,6 +50,74 @@ class Sample:
         self.condition = manifest_row[3]
 
 
+class _NativeIngest:
+    """sd_ingest_* handle: the junction union (pass 1) and the count matrix (pass 2)."""
+
+    _TYPE_CODE = {"SJ": 0, "splicedicebed": 1, "bed": 2, "leafcutter": 2}
+
+    def __init__(self, manifest, args):
+        import ctypes
+        from . import native
+        self._ct, self._native = ctypes, native
+        self.lib = native.load()
+        self.handle = ctypes.c_void_p(self.lib.sd_ingest_create())
+        self.manifest = manifest
+        motifs = _MOTIF_SETS[args.filter]
+        self.filter = native.QuantFilter(args.maxLength, args.minLength, args.minOverhang, args.minUnique,
+                                         int(bool(args.noMultimap)), int(bool(args.lowCoverageNan)),
+                                         sum(1 << m for m in motifs), 0, float(args.minEntropy))
+        n = len(manifest)
+        self.paths = (ctypes.c_char_p * n)(*[os.fsencode(s.filename) for s in manifest])
+        self.types = np.array([self._TYPE_CODE.get(s.type, -1) for s in manifest], dtype=np.int32)
+        self.threads = int(getattr(args, "threads", 0) or 0)
+
+    def __del__(self):
+        try:
+            self.lib.sd_ingest_destroy(self.handle)
+        except Exception:
+            pass
+
+    def _check(self, name, rc):
+        if rc != 0:
+            raise ValueError(f"{name}: {self._native.last_error()}")
+
+    def collect(self):
+        ct, native = self._ct, self._native
+        self._check("sd_ingest_collect", self.lib.sd_ingest_collect(
+            self.handle, len(self.manifest), self.paths, native.ptr(self.types), ct.byref(self.filter), self.threads))
+        n = self.lib.sd_ingest_junction_count(self.handle)
+        chrom = np.empty(n, dtype=np.int32); left = np.empty(n, dtype=np.int32)
+        right = np.empty(n, dtype=np.int32); strand = np.empty(n, dtype=np.int8)
+        self._check("sd_ingest_export", self.lib.sd_ingest_export(
+            self.handle, native.ptr(chrom), native.ptr(left), native.ptr(right), native.ptr(strand)))
+        names = [self.lib.sd_ingest_chrom_name(self.handle, i).decode() for i in range(self.lib.sd_ingest_chrom_count(self.handle))]
+        return {(names[c], l, r, chr(s)) for c, l, r, s in zip(chrom.tolist(), left.tolist(), right.tolist(), strand.tolist())}
+
+    def counts(self, rows):
+        """rows: junction tuples in output-row order -> (int32[J, S], low mask or None)."""
+        ct, native = self._ct, self._native
+        n = len(rows)
+        chrom_names = sorted({j[0] for j in rows})
+        lut = {c: i for i, c in enumerate(chrom_names)}
+        cnames = (ct.c_char_p * max(len(chrom_names), 1))(*[c.encode() for c in chrom_names])
+        chrom_of = np.fromiter((lut[j[0]] for j in rows), dtype=np.int32, count=n)
+        left = np.fromiter((j[1] for j in rows), dtype=np.int32, count=n)
+        right = np.fromiter((j[2] for j in rows), dtype=np.int32, count=n)
+        strand = np.fromiter((ord(j[3]) for j in rows), dtype=np.int8, count=n)
+        row = np.arange(n, dtype=np.int32)
+        self._check("sd_ingest_index", self.lib.sd_ingest_index(
+            self.handle, n, cnames, native.ptr(chrom_of), native.ptr(left), native.ptr(right), native.ptr(strand),
+            native.ptr(row)))
+        S = len(self.manifest)
+        counts = np.zeros((n, S), dtype=np.int32)
+        mask = np.zeros((n, S), dtype=np.uint8) if self.filter.low_coverage_nan else None
+        samples = np.arange(S, dtype=np.int32)
+        self._check("sd_ingest_counts", self.lib.sd_ingest_counts(
+            self.handle, S, self.paths, native.ptr(self.types), native.ptr(samples), ct.byref(self.filter),
+            native.ptr(counts), S, native.ptr(mask), S, self.threads))
+        return counts, mask
+
+
 class Timer:
     """Stage timer printing the reference's ``[h:mm:ss.ss]`` stamps (SPLICEDICE.py:48-66)."""
 
@@ -74,8 +142,9 @@ class SPLICEDICE:
     """The quant pipeline.  Constructing it runs every stage, like the reference class; pass
     ``run=False`` to drive the stages by hand (tests, library use)."""
 
-    def __init__(self, manifestFilename, outputPrefix, args, device=0, run=True):
+    def __init__(self, manifestFilename, outputPrefix, args, device=0, run=True, native_io=True):
         self.args = args
+        self.native_io = native_io
         self.manifestFilename = manifestFilename
         self.outputPrefix = outputPrefix
         self.device = device
@@ -163,7 +232,15 @@ class SPLICEDICE:
 
     def getAllJunctions(self):
         """Union over samples of the junctions that pass that sample's filter
-        (SPLICEDICE.py:147-228).  ``.bam`` / unknown-suffix samples contribute nothing."""
+        (SPLICEDICE.py:147-228).  ``.bam`` / unknown-suffix samples contribute nothing.
+        Native multi-threaded reader (sd_ingest_collect) unless ``native_io`` is off."""
+        if not self.native_io:
+            return self._getAllJunctions_py()
+        ing = self._ingest = _NativeIngest(self.manifest, self.args)
+        return ing.collect()
+
+    def _getAllJunctions_py(self):
+        """The same union with plain python line parsing (kept as the cross-check of the native reader)."""
         self._motifs = _MOTIF_SETS[self.args.filter]
         admit_by_type = {"SJ": self._admit_sj, "splicedicebed": self._admit_tagged_bed,
                          "bed": self._admit_plain_bed, "leafcutter": self._admit_plain_bed}
@@ -204,7 +281,15 @@ class SPLICEDICE:
     # ---------------------------------------------------------------- counts -------------
     def getJunctionCounts(self):
         """int32[J, S] of scores (last duplicate line wins) and the list of low cells
-        (SPLICEDICE.py:257-295)."""
+        (SPLICEDICE.py:257-295).  Native reader (sd_ingest_counts) unless ``native_io`` is off."""
+        if not self.native_io:
+            return self._getJunctionCounts_py()
+        ing = getattr(self, "_ingest", None) or _NativeIngest(self.manifest, self.args)
+        counts, mask = ing.counts(self._rows)
+        low = [tuple(x) for x in np.argwhere(mask).tolist()] if mask is not None else []
+        return counts, low
+
+    def _getJunctionCounts_py(self):
         index = self.junctionIndex
         a = self.args
         counts = np.zeros((len(index), len(self.manifest)), dtype=np.int32)
@@ -305,10 +390,13 @@ def add_parser(parser):
     parser.add_argument("--lowCoverageNan", action="store_true", help="NaN for cells scored below minUnique")
     parser.add_argument("--minEntropy", type=float, default=1, help="least Shannon diversity of read offsets")
     parser.add_argument("--device", type=int, default=0, help="CUDA device ordinal")
+    parser.add_argument("--threads", type=int, default=0, help="host threads for file parsing (0 = all)")
+    parser.add_argument("--pythonIO", action="store_true", help="read the sample files with the plain python parser")
 
 
 def run_with(args):
-    SPLICEDICE(args.manifest, args.output_prefix, args, device=getattr(args, "device", 0))
+    SPLICEDICE(args.manifest, args.output_prefix, args, device=getattr(args, "device", 0),
+               native_io=not getattr(args, "pythonIO", False))
 
 
 if __name__ == "__main__":

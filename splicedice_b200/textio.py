@@ -11,10 +11,11 @@ from . import native
 _KINDS = {np.dtype(np.float32): 0, np.dtype(np.float64): 1, np.dtype(np.int32): 2}
 
 
-def format_rows(matrix, names=None, threads=0) -> bytes:
-    """b"name\\tv\\tv...\\n" for every row of a 2-D float32 / float64 ('.3f') or int32 matrix."""
+def format_rows(matrix, names=None, threads=0, repr_floats=False) -> bytes:
+    """b"name\\tv\\tv...\\n" for every row of a 2-D float32 / float64 ('.3f') or int32 matrix;
+    ``repr_floats``: float64 as python's str(p) (the pairwise writer)."""
     m = np.asarray(matrix)
-    if m.ndim != 2 or m.dtype not in _KINDS:
+    if m.ndim != 2 or m.dtype not in _KINDS or (repr_floats and m.dtype != np.float64):
         raise TypeError("format_rows: 2-D float32 / float64 / int32 matrix expected")
     if m.strides[1] != m.itemsize:
         m = np.ascontiguousarray(m)
@@ -29,12 +30,12 @@ def format_rows(matrix, names=None, threads=0) -> bytes:
         off = np.zeros(rows + 1, dtype=np.int64)
         np.cumsum([len(e) for e in enc], out=off[1:])
         blob = b"".join(enc)
-    cap = rows * (cols * 7 + 40) + (len(blob) if blob else 0) + 64
+    cap = rows * (cols * (26 if repr_floats else 7) + 40) + (len(blob) if blob else 0) + 64
     lib = native.load()
     for _ in range(2):
         buf = ctypes.create_string_buffer(cap)
         written = ctypes.c_size_t()
-        rc = lib.sd_host_format_rows(_KINDS[m.dtype], native.ptr(m), rows, cols, m.strides[0] // m.itemsize,
+        rc = lib.sd_host_format_rows(3 if repr_floats else _KINDS[m.dtype], native.ptr(m), rows, cols, m.strides[0] // m.itemsize,
                                      blob, native.ptr(off), buf, cap, ctypes.byref(written), threads)
         if rc == native.SD_OK:
             return buf.raw[:written.value]
@@ -44,9 +45,9 @@ def format_rows(matrix, names=None, threads=0) -> bytes:
     raise native.NativeCallError("sd_host_format_rows", rc, native.last_error())
 
 
-def write_matrix(path, header: str, names, matrix, chunk_rows=65536, threads=0):
+def write_matrix(path, header: str, names, matrix, chunk_rows=65536, threads=0, repr_floats=False):
     """header line + one formatted row per junction, streamed in row chunks."""
     with open(path, "wb") as out:
         out.write(header.encode())
         for r0 in range(0, matrix.shape[0], chunk_rows):
-            out.write(format_rows(matrix[r0:r0 + chunk_rows], names[r0:r0 + chunk_rows], threads))
+            out.write(format_rows(matrix[r0:r0 + chunk_rows], names[r0:r0 + chunk_rows], threads, repr_floats))

@@ -149,3 +149,86 @@ def test_native_row_formatter_is_byte_identical_to_python():
     want = "".join("\t".join(f"{float(v):.0f}" for v in row) + "\n" for row in z.tolist())
     assert textio.format_rows(z) == want.encode()
     assert textio.format_rows(np.zeros((0, 5), dtype=np.float32), []) == b""
+
+
+def test_pairwise_value_formatter_matches_str():
+    from splicedice_b200 import textio
+    rng = np.random.default_rng(1)
+    y = np.concatenate([rng.random(50000), 10.0 ** rng.uniform(-320, 300, 50000),
+                        np.array([1.0, 0.5, 1e-5, 1e-4, 1e16, 1e15, 9999999999999998.0, 1e22, 5e-324, 0.1, 1 / 3,
+                                  np.inf, -np.inf, np.nan, 0.0, -0.0, -1.5e-10, 100.0, 12345.678])])
+    y = np.concatenate([y, np.ones((-len(y)) % 30)]).reshape(-1, 30)
+    want = "".join("\t".join(str(np.float64(v)) for v in row) + "\n" for row in y)
+    assert textio.format_rows(y, repr_floats=True) == want.encode()
+
+
+def _quant_job(manifest, out, extra=(), native_io=True):
+    import argparse
+    from splicedice_b200 import quant
+    p = argparse.ArgumentParser()
+    quant.add_parser(p)
+    args = p.parse_args(["-m", str(manifest), "-o", str(out), *extra])
+    job = quant.SPLICEDICE(args.manifest, args.output_prefix, args, run=False, native_io=native_io)
+    job.manifest = job.parseManifest()
+    return job
+
+
+def test_native_ingest_equals_python_parsers(tmp_path, golden_dir):
+    """sd_ingest_collect / sd_ingest_counts against the per-line python readers on every sample
+    type, with duplicates, filters at their boundaries and low-coverage cells."""
+    rng = np.random.default_rng(5)
+    sj = tmp_path / "a.SJ.out.tab"
+    lines = []
+    for i in range(3000):
+        start = int(rng.integers(1, 5000)); length = int(rng.integers(40, 70)) if i % 3 else int(rng.integers(49000, 50010))
+        lines.append(f"chr{rng.integers(1, 4)}\t{start}\t{start + length - 1}\t{rng.integers(0, 3)}\t{rng.integers(0, 7)}\t0\t"
+                     f"{rng.integers(0, 9)}\t{rng.integers(0, 4)}\t{rng.integers(1, 30)}\n")
+    sj.write_text("".join(lines))
+    bed = tmp_path / "b.junc.bed"
+    lines = []
+    for i in range(3000):
+        left = int(rng.integers(0, 5000)); length = int(rng.integers(45, 60))
+        lines.append(f"chr{rng.integers(1, 4)}\t{left}\t{left + length}\tj{i}\t{rng.integers(0, 12)}\t{'+-.'[int(rng.integers(0, 3))]}\n")
+    lines += lines[:200]                                       # duplicates: last line wins
+    bed.write_text("".join(lines))
+    tag = tmp_path / "c.bed"
+    lines = []
+    for i in range(3000):
+        left = int(rng.integers(0, 5000)); length = int(rng.integers(45, 60))
+        ann = "?" if i % 2 else "GENE1"
+        lines.append(f"chr{rng.integers(1, 4)}\t{left}\t{left + length}\te:{rng.random() * 2:.2f}:{rng.random() * 2:.2f};"
+                     f"o:{rng.integers(0, 12)};m:GT_AG;a:{ann}\t{rng.integers(0, 12)}\t{'+-'[int(rng.integers(0, 2))]}\n")
+    tag.write_text("".join(lines))
+    leaf = tmp_path / "d.leafcutter.junc"
+    leaf.write_text("".join(f"chrX\t{100 * i}\t{100 * i + 55 + i % 3}\t.\t{i % 9}\t+\n" for i in range(500)))
+    ignored = tmp_path / "e.junc"
+    ignored.write_text("not a junction file\n")
+    man = tmp_path / "m.txt"
+    man.write_text("".join(f"s{i}\t{p}\tmeta\tcond\n" for i, p in enumerate([sj, bed, tag, leaf, ignored])))
+    for extra in ((), ("--lowCoverageNan", "--minUnique", "7"), ("--noMultimap", "--minLength", "48", "--maxLength", "56"),
+                  ("--minEntropy", "0.5", "--minOverhang", "8")):
+        fast = _quant_job(man, tmp_path / "o", extra, native_io=True)
+        slow = _quant_job(man, tmp_path / "o", extra, native_io=False)
+        fast.junctions = fast.getAllJunctions()
+        slow.junctions = slow.getAllJunctions()
+        assert fast.junctions == slow.junctions and len(fast.junctions) > 500
+        rows = sorted(fast.junctions)
+        for job in (fast, slow):
+            job._rows = rows
+            job.junctionIndex = {j: r for r, j in enumerate(rows)}
+        c_fast, low_fast = fast.getJunctionCounts()
+        c_slow, low_slow = slow.getJunctionCounts()
+        np.testing.assert_array_equal(c_fast, c_slow)
+        assert sorted(set(low_fast)) == sorted(set(low_slow))
+        assert (c_fast[:, 4] == 0).all()                       # the unknown-suffix sample stays a zero column
+
+
+def test_native_ingest_reports_malformed_lines(tmp_path):
+    bad = tmp_path / "bad.junc.bed"
+    bad.write_text("chr1\t10\t90\tj\t5\t+\nchr1\tten\t90\tj\t5\t+\n")
+    man = tmp_path / "m.txt"
+    man.write_text(f"s0\t{bad}\tm\tc\n")
+    job = _quant_job(man, tmp_path / "o")
+    with pytest.raises(ValueError) as e:
+        job.getAllJunctions()
+    assert "bad.junc.bed:2" in str(e.value)
