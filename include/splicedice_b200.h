@@ -189,6 +189,18 @@ int sd_host_format_rows(int kind, const void *matrix, int64_t rows, int32_t cols
                         const char *names, const int64_t *name_off, char *out, size_t cap,
                         size_t *written, int n_threads);
 
+/* Table reader for "header\nname<TAB>v<TAB>...\n" files (the reference parses them one python
+ * float per cell: counts_to_ps.py:43-51, pairwise_fisher.py:46-61, ir_table.py:72-80).
+ * sd_host_table_open maps the file and reports its shape; sd_host_table_read fills the raw
+ * header line, the row names (concatenated, with offsets) and a float64 [rows, cols] matrix on
+ * n_threads threads; ragged rows / non-numeric fields fail with SD_ERR_INVALID.
+ */
+void *sd_host_table_open(const char *path, int64_t *rows, int32_t *cols, int64_t *header_bytes,
+                         int64_t *name_bytes);
+void sd_host_table_close(void *handle);
+int sd_host_table_read(void *handle, char *header, char *names, int64_t *name_off, double *values,
+                       int64_t ld, int32_t n_threads);
+
 /* ---- host-side sample-file ingest for quant (no CUDA) ------------------------------------
  * Replaces the per-line python passes SPLICEDICE.getAllJunctions (SPLICEDICE.py:147-228) and
  * SPLICEDICE.getJunctionCounts (SPLICEDICE.py:257-295): memory-mapped files, several threads,

@@ -46,14 +46,11 @@ def determine_clusters(counts_file, device=0):
 
 
 def get_counts(count_file):
-    """(header line, name -> float64 row); a repeated name keeps its last row."""
-    with open(count_file) as handle:
-        header = handle.readline()
-        counts = {}
-        for line in handle:
-            row = line.rstrip().split("\t")
-            counts[row[0]] = np.array(row[1:], dtype=float)
-    return header, counts
+    """(header line, name -> float64 row); a repeated name keeps its last row.  Parsed natively
+    (sd_host_table_read)."""
+    from . import textio
+    header, names, values = textio.read_table(count_file)
+    return header, {n: values[i] for i, n in enumerate(names)}
 
 
 def junctionStringToTuple(string):

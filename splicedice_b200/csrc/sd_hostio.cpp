@@ -186,3 +186,173 @@ extern "C" int sd_host_format_rows(int kind, const void *matrix, int64_t rows, i
     }
     return SD_OK;
 }
+
+// ---- table reader -------------------------------------------------------------------------
+// "header\nname<TAB>v<TAB>v...\n" files (the reference's _inclusionCounts.tsv and friends, read
+// there one python float per cell: counts_to_ps.py:43-51, pairwise_fisher.py:46-61,
+// ir_table.py:72-80).  The file is memory-mapped, line starts are indexed once, and the value
+// fields are parsed on several threads into a dense float64 matrix.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+namespace {
+
+struct TableFile {
+    const char *data = nullptr;
+    size_t size = 0;
+    int fd = -1;
+    std::vector<size_t> line_start;     // data rows only (header excluded); one extra entry = end
+    size_t header_end = 0;              // offset one past the header line's '\n' (or size)
+    int32_t cols = 0;
+    int64_t name_bytes = 0;
+    ~TableFile()
+    {
+        if (data) munmap(const_cast<char *>(data), size);
+        if (fd >= 0) close(fd);
+    }
+};
+
+inline const char *rstrip(const char *p, const char *end)
+{
+    while (end > p && (end[-1] == ' ' || end[-1] == '\t' || end[-1] == '\r' || end[-1] == '\n' || end[-1] == '\f' ||
+                       end[-1] == '\v'))
+        --end;
+    return end;
+}
+
+// python float(): plain digits fast, everything else through strtod
+inline bool parse_value(const char *p, const char *e, double *out)
+{
+    if (p == e) return false;
+    const char *q = p;
+    uint64_t v = 0;
+    int digits = 0;
+    while (q < e && *q >= '0' && *q <= '9' && digits < 18) { v = v * 10 + (uint64_t)(*q - '0'); ++q; ++digits; }
+    if (q == e && digits) { *out = (double)v; return true; }
+    char buf[96];
+    const size_t n = (size_t)(e - p);
+    if (n >= sizeof buf) return false;
+    memcpy(buf, p, n);
+    buf[n] = 0;
+    char *endp = nullptr;
+    *out = strtod(buf, &endp);
+    while (*endp == ' ') ++endp;
+    return endp == buf + n && endp != buf;
+}
+
+}  // namespace
+
+extern "C" {
+
+void *sd_host_table_open(const char *path, int64_t *rows, int32_t *cols, int64_t *header_bytes, int64_t *name_bytes)
+{
+    if (!path || !rows || !cols || !header_bytes || !name_bytes) {
+        sd::fail(SD_ERR_INVALID, "sd_host_table_open: null pointer");
+        return nullptr;
+    }
+    TableFile *t = new TableFile();
+    t->fd = ::open(path, O_RDONLY);
+    struct stat st;
+    if (t->fd < 0 || fstat(t->fd, &st) != 0) {
+        sd::fail(SD_ERR_INVALID, "sd_host_table_open: cannot open %s", path);
+        delete t;
+        return nullptr;
+    }
+    t->size = (size_t)st.st_size;
+    if (t->size) {
+        void *p = mmap(nullptr, t->size, PROT_READ, MAP_PRIVATE, t->fd, 0);
+        if (p == MAP_FAILED) {
+            sd::fail(SD_ERR_INVALID, "sd_host_table_open: cannot map %s", path);
+            delete t;
+            return nullptr;
+        }
+        t->data = static_cast<const char *>(p);
+    }
+    const char *end = t->data + t->size;
+    const char *nl = t->size ? (const char *)memchr(t->data, '\n', t->size) : nullptr;
+    t->header_end = nl ? (size_t)(nl - t->data) + 1 : t->size;
+    for (const char *p = t->data + t->header_end; p < end;) {
+        t->line_start.push_back((size_t)(p - t->data));
+        const char *n2 = (const char *)memchr(p, '\n', (size_t)(end - p));
+        p = n2 ? n2 + 1 : end;
+    }
+    t->line_start.push_back(t->size);
+    // columns from the first data row; names measured on every row
+    const int64_t n_rows = (int64_t)t->line_start.size() - 1;
+    for (int64_t r = 0; r < n_rows; ++r) {
+        const char *p = t->data + t->line_start[(size_t)r];
+        const char *e = rstrip(p, t->data + t->line_start[(size_t)r + 1]);
+        const char *tab = (const char *)memchr(p, '\t', (size_t)(e - p));
+        t->name_bytes += (tab ? tab : e) - p;
+        if (r == 0) {
+            int32_t c = 0;
+            for (const char *q = p; q < e; ++q) c += *q == '\t';
+            t->cols = c;
+        }
+    }
+    *rows = n_rows;
+    *cols = t->cols;
+    *header_bytes = (int64_t)t->header_end;
+    *name_bytes = t->name_bytes;
+    return t;
+}
+
+void sd_host_table_close(void *handle) { delete static_cast<TableFile *>(handle); }
+
+// header: the raw first line (header_bytes, newline included); names: concatenated row names with
+// name_off[rows + 1]; values: float64 [rows, cols] with leading dimension ld.  A row whose field
+// count differs from the first row's, or a field python's float() would reject, fails the call.
+int sd_host_table_read(void *handle, char *header, char *names, int64_t *name_off, double *values, int64_t ld,
+                       int32_t n_threads)
+{
+    SD_REQUIRE(handle && name_off, "sd_host_table_read: null pointer");
+    TableFile *t = static_cast<TableFile *>(handle);
+    const int64_t rows = (int64_t)t->line_start.size() - 1;
+    SD_REQUIRE(rows == 0 || t->cols == 0 || (values && ld >= t->cols), "sd_host_table_read: bad value buffer");
+    if (header && t->header_end) memcpy(header, t->data, t->header_end);
+    name_off[0] = 0;
+    for (int64_t r = 0; r < rows; ++r) {
+        const char *p = t->data + t->line_start[(size_t)r];
+        const char *e = rstrip(p, t->data + t->line_start[(size_t)r + 1]);
+        const char *tab = (const char *)memchr(p, '\t', (size_t)(e - p));
+        const int64_t n = (tab ? tab : e) - p;
+        if (names) memcpy(names + name_off[r], p, (size_t)n);
+        name_off[r + 1] = name_off[r] + n;
+    }
+    if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    n_threads = (int)std::max<int64_t>(1, std::min<int64_t>(n_threads, rows / 256));
+    std::vector<int64_t> bad((size_t)n_threads, -1);
+    auto work = [&](int w) {
+        const int64_t r0 = rows * w / n_threads, r1 = rows * (w + 1) / n_threads;
+        for (int64_t r = r0; r < r1; ++r) {
+            const char *p = t->data + t->line_start[(size_t)r];
+            const char *e = rstrip(p, t->data + t->line_start[(size_t)r + 1]);
+            const char *q = (const char *)memchr(p, '\t', (size_t)(e - p));
+            int32_t c = 0;
+            while (q) {
+                const char *s = q + 1;
+                const char *nx = (const char *)memchr(s, '\t', (size_t)(e - s));
+                const char *fe = nx ? nx : e;
+                if (c >= t->cols || !parse_value(s, fe, values + r * ld + c)) { bad[(size_t)w] = r; return; }
+                ++c;
+                q = nx;
+            }
+            if (c != t->cols) { bad[(size_t)w] = r; return; }
+        }
+    };
+    if (n_threads == 1) work(0);
+    else {
+        std::vector<std::thread> pool;
+        for (int w = 0; w < n_threads; ++w) pool.emplace_back(work, w);
+        for (auto &th : pool) th.join();
+    }
+    for (int64_t b : bad)
+        if (b >= 0)
+            return sd::fail(SD_ERR_INVALID, "sd_host_table_read: data row %lld is ragged or holds a non-numeric field",
+                            (long long)(b + 1));
+    return SD_OK;
+}
+
+}  // extern "C"

@@ -58,16 +58,26 @@ def getAnnotated(annotation):
     return annotated
 
 
+class _SampleCounts:
+    """junction name -> float count of one sample: a column of the parsed table."""
+
+    def __init__(self, rows, values, col):
+        self._rows, self._values, self._col = rows, values, col
+
+    def __contains__(self, name):
+        return name in self._rows
+
+    def __getitem__(self, name):
+        return float(self._values[self._rows[name], self._col])
+
+
 def getInclusionCounts(filename):
-    """sample -> {junction name -> float count} (ir_table.py:72-80)."""
-    with open(filename) as handle:
-        header = handle.readline().strip().split("\t")
-        counts = {s: {} for s in header[1:]}
-        for line in handle:
-            row = line.rstrip().split("\t")
-            for s, value in zip(header[1:], row[1:]):
-                counts[s][row[0]] = float(value)
-    return counts
+    """sample -> {junction name -> float count} (ir_table.py:72-80), as column views over the
+    natively parsed table (sd_host_table_read)."""
+    from . import textio
+    header, names, values = textio.read_table(filename)
+    rows = {n: i for i, n in enumerate(names)}
+    return {s: _SampleCounts(rows, values, c) for c, s in enumerate(header.strip().split("\t")[1:])}
 
 
 def getClusters(filename):

@@ -58,6 +58,9 @@ _SIGNATURES = {
     "sd_ir_ratio": (c_int, [c_int64, c_int32, _P, c_int64, _P, c_int64, _P, _P, _P, c_int64,
                             c_int64, c_int64, _P]),
     "sd_rsd5": (c_int, [c_int64, _P, _P, _P]),
+    "sd_host_table_open": (c_void_p, [c_char_p, POINTER(c_int64), POINTER(c_int32), POINTER(c_int64), POINTER(c_int64)]),
+    "sd_host_table_close": (None, [_P]),
+    "sd_host_table_read": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int32]),
     "sd_ingest_create": (c_void_p, []),
     "sd_ingest_destroy": (None, [_P]),
     "sd_ingest_collect": (c_int, [_P, c_int32, _P, _P, _P, c_int32]),

@@ -28,16 +28,16 @@ def getClusters(filename, filter_list=None):
 
 
 def getEventCounts(filename, filter_list=None):
-    """(sample names, event names, float64 counts); with a filter only listed events are kept."""
-    events, rows = [], []
-    with open(filename) as handle:
-        samples = handle.readline().rstrip().split("\t")[1:]
-        for line in handle:
-            row = line.rstrip().split("\t")
-            if filter_list is None or row[0] in filter_list:
-                events.append(row[0])
-                rows.append(row[1:])
-    return samples, events, np.array(rows, dtype=float)
+    """(sample names, event names, float64 counts); with a filter only listed events are kept.
+    Parsed natively (sd_host_table_read); same results as the reference's per-line reader."""
+    from . import textio
+    header, events, counts = textio.read_table(filename)
+    samples = header.rstrip().split("\t")[1:]
+    if filter_list is not None:
+        keep = [i for i, e in enumerate(events) if e in filter_list]
+        events = [events[i] for i in keep]
+        counts = counts[keep]
+    return samples, events, counts
 
 
 def fdr_bh(p):

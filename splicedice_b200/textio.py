@@ -51,3 +51,30 @@ def write_matrix(path, header: str, names, matrix, chunk_rows=65536, threads=0, 
         out.write(header.encode())
         for r0 in range(0, matrix.shape[0], chunk_rows):
             out.write(format_rows(matrix[r0:r0 + chunk_rows], names[r0:r0 + chunk_rows], threads, repr_floats))
+
+
+def read_table(path, threads=0):
+    """(raw header line, row names, float64 [rows, cols] matrix) of a name<TAB>values table,
+    parsed natively (sd_host_table_*).  ValueError on ragged rows / non-numeric fields."""
+    import os
+    lib = native.load()
+    rows, cols = ctypes.c_int64(), ctypes.c_int32()
+    hbytes, nbytes = ctypes.c_int64(), ctypes.c_int64()
+    handle = lib.sd_host_table_open(os.fsencode(path), ctypes.byref(rows), ctypes.byref(cols), ctypes.byref(hbytes),
+                                    ctypes.byref(nbytes))
+    if not handle:
+        raise FileNotFoundError(native.last_error())
+    handle = ctypes.c_void_p(handle)
+    try:
+        header = ctypes.create_string_buffer(max(hbytes.value, 1))
+        names = ctypes.create_string_buffer(max(nbytes.value, 1))
+        off = np.zeros(rows.value + 1, dtype=np.int64)
+        values = np.empty((rows.value, cols.value), dtype=np.float64)
+        rc = lib.sd_host_table_read(handle, header, names, native.ptr(off), native.ptr(values), max(cols.value, 1), threads)
+        if rc != native.SD_OK:
+            raise ValueError(native.last_error())
+        blob = names.raw[:nbytes.value]
+        o = off.tolist()
+        return header.raw[:hbytes.value].decode(), [blob[o[i]:o[i + 1]].decode() for i in range(rows.value)], values
+    finally:
+        lib.sd_host_table_close(handle)

@@ -232,3 +232,27 @@ def test_native_ingest_reports_malformed_lines(tmp_path):
     with pytest.raises(ValueError) as e:
         job.getAllJunctions()
     assert "bad.junc.bed:2" in str(e.value)
+
+
+def test_native_table_reader(tmp_path, golden_dir):
+    from splicedice_b200 import textio
+    exp = os.path.join(golden_dir, "cli_8x", "expected", "ref_inclusionCounts.tsv")
+    header, names, values = textio.read_table(exp)
+    lines = open(exp).read().split("\n")
+    assert header == lines[0] + "\n" and names == [l.split("\t")[0] for l in lines[1:] if l]
+    want = np.array([[float(x) for x in l.split("\t")[1:]] for l in lines[1:] if l])
+    np.testing.assert_array_equal(values, want)
+    odd = tmp_path / "odd.tsv"
+    odd.write_text("h\ta\tb\nx\t1.5\t2e3\ny\tnan\t-0.0\nz\t007\t1e-3")           # no trailing newline
+    h, n, v = textio.read_table(str(odd))
+    assert n == ["x", "y", "z"] and v[0].tolist() == [1.5, 2000.0] and np.isnan(v[1, 0]) and v[2].tolist() == [7.0, 0.001]
+    ragged = tmp_path / "ragged.tsv"
+    ragged.write_text("h\ta\tb\nx\t1\t2\ny\t1\n")
+    with pytest.raises(ValueError):
+        textio.read_table(str(ragged))
+    with pytest.raises(FileNotFoundError):
+        textio.read_table(str(tmp_path / "missing.tsv"))
+    empty = tmp_path / "empty.tsv"
+    empty.write_text("cluster\ts0\n")
+    h, n, v = textio.read_table(str(empty))
+    assert h == "cluster\ts0\n" and n == [] and v.shape[0] == 0
