@@ -26,21 +26,33 @@ __device__ __noinline__ double lgfact_fallback(double k) { return lgamma(k + 1.0
 
 template <int kMode>
 struct DeviceTable {
-    const double2 *smem;     // staged prefix
+    uint32_t smem;           // shared-window address of the staged prefix (32-bit: plain LDS, no generic loads)
     const double2 *gmem;     // full table
     int64_t n_smem, n_gmem;
+    __device__ __forceinline__ static double2 lds2(uint32_t addr)
+    {
+        double2 v;
+        asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+        return v;
+    }
+    __device__ __forceinline__ static double lds1(uint32_t addr)
+    {
+        double v;
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+        return v;
+    }
     template <class Int>
     __device__ __forceinline__ double2 load(Int k) const
     {
-        if (kMode == 0) return smem[k];
-        if ((int64_t)k < n_smem) return smem[k];
+        if (kMode == 0) return lds2(smem + (uint32_t)k * 16u);
+        if ((int64_t)k < n_smem) return lds2(smem + (uint32_t)k * 16u);
         if (kMode == 1 || (int64_t)k < n_gmem) return __ldg(gmem + k);
         return make_double2(lgfact_fallback((double)k), 0.0);
     }
     template <class Int>
     __device__ __forceinline__ double hi(Int k) const
     {
-        if (kMode == 0) return reinterpret_cast<const double *>(smem)[2 * (int64_t)k];
+        if (kMode == 0) return lds1(smem + (uint32_t)k * 16u);
         return load(k).x;
     }
     template <class Int>
@@ -81,7 +93,7 @@ __global__ void __launch_bounds__(kFisherThreads, 3) fisher_pairwise_kernel(cons
 {
     extern __shared__ __align__(16) double2 s_tab[];
     stage_table(s_tab, p.table, p.smem_entries);
-    const DeviceTable<kMode> tab{s_tab, p.table, p.smem_entries, p.table_entries};
+    const DeviceTable<kMode> tab{smem_u32(s_tab), p.table, p.smem_entries, p.table_entries};
 
     const int lane = threadIdx.x & 31;
     const int64_t tiles_per_row = (p.n_pairs + 31) / 32;
@@ -116,7 +128,7 @@ __global__ void __launch_bounds__(kFisherThreads, 2) fisher_tables_kernel(
 {
     extern __shared__ __align__(16) double2 s_tab[];
     stage_table(s_tab, table, smem_entries);
-    const DeviceTable<kMode> tab{s_tab, table, smem_entries, table_entries};
+    const DeviceTable<kMode> tab{smem_u32(s_tab), table, smem_entries, table_entries};
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
         out[i] = fisher::two_sided<Int>(tab, (Int)a[i], (Int)b[i], (Int)c[i], (Int)d[i]);
