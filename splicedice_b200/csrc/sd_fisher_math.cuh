@@ -132,6 +132,18 @@ SD_HD double tail_fast(double p, double q, double u, double v)
     return t.A / t.Q;
 }
 
+// f(x) = log(pmf(x) / pmf(a)) in double-double.  Out of line, with everything passed by value,
+// so the (rare) call does not force the caller's state into local memory.
+template <class Table, class Int>
+SD_NOINLINE dd f_exact_of(Table tab, Int a, Int b, Int c, Int d, Int n1, Int n2, Int n, Int x)
+{
+    dd s = dd_sub(tab.get(a), tab.get(x));
+    s = dd_add(s, dd_sub(tab.get(b), tab.get(n1 - x)));
+    s = dd_add(s, dd_sub(tab.get(c), tab.get(n - x)));
+    s = dd_add(s, dd_sub(tab.get(d), tab.get(n2 - n + x)));
+    return s;
+}
+
 // G(x) = lg[x] + lg[n1-x] + lg[n-x] + lg[n2-n+x]; log pmf(x) = const - G(x).
 // Int is the integer type of the table entries (int32_t when every table total fits 31 bits).
 template <class Table, class Int>
@@ -147,14 +159,7 @@ struct Problem {
         return (tab.hi(a) - tab.hi(x)) + (tab.hi(b) - tab.hi(n1 - x)) + (tab.hi(c) - tab.hi(n - x)) +
                (tab.hi(d) - tab.hi(n2 - n + x));
     }
-    SD_NOINLINE dd f_exact(Int x) const
-    {
-        dd s = dd_sub(tab.get(a), tab.get(x));
-        s = dd_add(s, dd_sub(tab.get(b), tab.get(n1 - x)));
-        s = dd_add(s, dd_sub(tab.get(c), tab.get(n - x)));
-        s = dd_add(s, dd_sub(tab.get(d), tab.get(n2 - n + x)));
-        return s;
-    }
+    SD_HD dd f_exact(Int x) const { return f_exact_of<Table, Int>(tab, a, b, c, d, n1, n2, n, x); }
     // scipy's far-side admission test: pmf(x) <= pexact * (1 + 1e-14)
     SD_HD bool admitted(Int x) const
     {

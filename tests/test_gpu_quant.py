@@ -49,7 +49,7 @@ def test_golden_ps_bits(name, variant):
 
 
 @pytest.mark.parametrize("shape", [(5000, 8), (3000, 64), (2500, 130), (1200, 1000), (700, 1001), (64, 3), (1, 1),
-                                   (4000, 260)])
+                                   (4000, 260), (900, 100), (500, 65), (33, 193), (2100, 512)])
 @pytest.mark.parametrize("variant", ["tiled", "gather"])
 def test_oracle_parity(shape, variant):
     native, ops = _ops()
