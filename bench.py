@@ -488,7 +488,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "int64 sums, f32 PS", "data": "synthetic",
+            "vs_baseline": None, "dtype": "i32/i64 sums, f32 divide", "data": "synthetic",
             "config": {"workload": f"quant PS: {S} samples x {args.junctions} junctions per GPU (configs[1])",
                        "junctions_total": J_total, "nnz": int(row_ptr[-1]), "slabs": parts,
                        "l2": "inputs+outputs 3.2 GB per pass >> 126 MB L2, no flush", "seed": SEED,

@@ -395,8 +395,15 @@ int sd_fisher_pairwise_host(int device, int64_t n_junctions, int32_t n_samples, 
         for (auto e : ev) cudaEventDestroy(e);
         if (s_out) cudaStreamSynchronize(s_out);
         if (s_k) cudaStreamSynchronize(s_k);
-        cudaFree(d_inc); cudaFree(d_exc); cudaFree(d_pa); cudaFree(d_pb); cudaFree(d_p);
-        if (s_k) cudaStreamDestroy(s_k);
+        if (s_k) {
+            if (d_inc) cudaFreeAsync(d_inc, s_k);
+            if (d_exc) cudaFreeAsync(d_exc, s_k);
+            if (d_pa) cudaFreeAsync(d_pa, s_k);
+            if (d_pb) cudaFreeAsync(d_pb, s_k);
+            if (d_p) cudaFreeAsync(d_p, s_k);
+            cudaStreamSynchronize(s_k);
+            cudaStreamDestroy(s_k);
+        }
         if (s_out) cudaStreamDestroy(s_out);
         cudaSetDevice(prev_dev);
     };
@@ -412,14 +419,22 @@ int sd_fisher_pairwise_host(int device, int64_t n_junctions, int32_t n_samples, 
     } while (0)
     SD_TRY(cudaStreamCreateWithFlags(&s_k, cudaStreamNonBlocking));
     SD_TRY(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
-    // p-value blocks of ~64 MB, double buffered
-    int64_t block_rows = std::max<int64_t>(1, (int64_t)(64u << 20) / (n_pairs * 8));
+    // p-value blocks of ~64 MB, double buffered (tuning knob for experiments: SD_FISHER_HOST_BLOCK_MB)
+    int64_t block_mb = 64;
+    if (const char *env = getenv("SD_FISHER_HOST_BLOCK_MB")) block_mb = std::max<int64_t>(1, atoll(env));
+    int64_t block_rows = std::max<int64_t>(1, (block_mb << 20) / (n_pairs * 8));
     block_rows = std::min(block_rows, J);
-    SD_TRY(cudaMalloc(&d_inc, (size_t)J * n_samples * 4));
-    SD_TRY(cudaMalloc(&d_exc, (size_t)J * n_samples * 8));
-    SD_TRY(cudaMalloc(&d_pa, (size_t)n_pairs * 4));
-    SD_TRY(cudaMalloc(&d_pb, (size_t)n_pairs * 4));
-    SD_TRY(cudaMalloc(&d_p, (size_t)2 * block_rows * n_pairs * 8));
+    {   // keep freed blocks in the default pool so repeated calls do not pay cudaMalloc again
+        cudaMemPool_t pool;
+        SD_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t keep = ~0ull;
+        SD_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
+    SD_TRY(cudaMallocAsync(&d_inc, (size_t)J * n_samples * 4, s_k));
+    SD_TRY(cudaMallocAsync(&d_exc, (size_t)J * n_samples * 8, s_k));
+    SD_TRY(cudaMallocAsync(&d_pa, (size_t)n_pairs * 4, s_k));
+    SD_TRY(cudaMallocAsync(&d_pb, (size_t)n_pairs * 4, s_k));
+    SD_TRY(cudaMallocAsync(&d_p, (size_t)2 * block_rows * n_pairs * 8, s_k));
     SD_TRY(cudaMemcpy2DAsync(d_inc, (size_t)n_samples * 4, inc, (size_t)ld_inc * 4, (size_t)n_samples * 4, (size_t)J,
                              cudaMemcpyHostToDevice, s_k));
     SD_TRY(cudaMemcpy2DAsync(d_exc, (size_t)n_samples * 8, exc, (size_t)ld_exc * 8, (size_t)n_samples * 8, (size_t)J,
