@@ -175,6 +175,14 @@ def fisher_work(a, b, c, d):
     return float(terms.mean()), float(support.mean()), float(trivial.mean())
 
 
+def config_label(samples, junctions_total):
+    if samples == 1000 and junctions_total % 400_000 == 0:
+        return "BASELINE.json configs[1], GTEx-scale"
+    if samples == 10_000 and junctions_total == 1_000_000:
+        return "BASELINE.json configs[3], TCGA-scale, cluster-sharded"
+    return "custom shape"
+
+
 def ncu_traffic(rows, samples):
     """dram__bytes_read + dram__bytes_write of one launch from the committed ncu capture
     (profiles/), valid only for the shape it was taken on."""
@@ -489,9 +497,9 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "i32/i64 sums, f32 divide", "data": "synthetic",
-            "config": {"workload": f"quant PS: {S} samples x {args.junctions} junctions per GPU (configs[1])",
+            "config": {"workload": f"quant PS: {S} samples x {args.junctions} junctions per GPU ({config_label(S, J_total)})",
                        "junctions_total": J_total, "nnz": int(row_ptr[-1]), "slabs": parts,
-                       "l2": "inputs+outputs 3.2 GB per pass >> 126 MB L2, no flush", "seed": SEED,
+                       "l2": f"inputs+outputs {cells_rank * 8 / 1e9:.1f} GB per pass per GPU >> 126 MB L2, no flush", "seed": SEED,
                        "cluster_build_ms": t_k1 * 1e3, "flags": args.flags},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "kernel": "quant_wide_kernel<2, true>", "kernel_ms": kernel_ms,
