@@ -256,7 +256,7 @@ def main():
     # 1. SURVEY §4 known-answer vector through the real file-based CLI path
     js = [(c, l, r, s) for c, l, r, s, _ in SURVEY_ROWS]
     counts = np.array([k for *_, k in SURVEY_ROWS], dtype=np.int64)
-    gen_cli_case("survey_vector", js, counts)
+    gen_cli_case("survey_vector", js, counts, quant_over=dict(drim=True))
 
     # 2. config-1 analogue, small: 8 samples x ~400 junctions (+ adversarial structures)
     rng = np.random.default_rng(8)

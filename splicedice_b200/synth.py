@@ -145,6 +145,6 @@ def adversarial_tuples(seed: int = 0):
     for _ in range(300):
         a = int(rng.integers(0, 5000))
         out.add((f"chr{int(rng.integers(1, 23))}", a, a + int(rng.integers(50, 900)), "+-"[int(rng.integers(0, 2))]))
-    out = list(out)
+    out = sorted(out)          # set order depends on string hashing: sort before shuffling
     rng.shuffle(out)
     return out

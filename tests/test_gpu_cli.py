@@ -45,9 +45,12 @@ def test_quant_files_are_byte_identical(case, golden_dir, tmp_path, capsys):
         argv.append("--lowCoverageNan")
     if "minUnique" in over:
         argv += ["--minUnique", str(over["minUnique"])]
+    if over.get("drim"):
+        argv.append("--drim")
     quant.run_with(_args(quant, argv))
     exp = os.path.join(case_dir, "expected")
-    for suffix in ("_allClusters.tsv", "_junctions.bed", "_inclusionCounts.tsv", "_allPS.tsv"):
+    suffixes = ("_allClusters.tsv", "_junctions.bed", "_inclusionCounts.tsv", "_allPS.tsv")
+    for suffix in suffixes + (("_drimTable.tsv",) if over.get("drim") else ()):
         _same(str(tmp_path / f"out{suffix}"), os.path.join(exp, f"ref{suffix}"))
     assert "All done" in capsys.readouterr().out
 
