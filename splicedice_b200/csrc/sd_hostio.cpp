@@ -120,9 +120,12 @@ void format_range(int64_t r0, int64_t r1, int32_t cols, const char *names, const
 {
     out->reserve((size_t)(r1 - r0) * ((size_t)cols * 8 + 32));
     for (int64_t r = r0; r < r1; ++r) {
-        if (names) out->append(names + name_off[r], (size_t)(name_off[r + 1] - name_off[r]));
+        if (names) {       // f"{name}\t{tab.join(values)}\n": the tab is there even without values
+            out->append(names + name_off[r], (size_t)(name_off[r + 1] - name_off[r]));
+            out->push_back('\t');
+        }
         for (int32_t c = 0; c < cols; ++c) {
-            if (names || c) out->push_back('\t');
+            if (c) out->push_back('\t');
             get(*out, r, c);
         }
         out->push_back('\n');

@@ -157,3 +157,27 @@ def test_cli_dispatcher(golden_dir, tmp_path):
     cli.main(["counts_to_ps", "-i", os.path.join(exp, "ref_inclusionCounts.tsv"), "-c",
               os.path.join(exp, "ref_allClusters.tsv"), "-o", str(tmp_path / "x")])
     _same(str(tmp_path / "x_allPS.tsv"), os.path.join(exp, "c2ps_c_allPS.tsv"))
+
+
+def test_degenerate_inputs(tmp_path):
+    """No junction survives the filters / a single sample: the files the reference would write
+    (headers only; a trailing tab where the value list is empty)."""
+    from splicedice_b200 import pairwise_fisher, quant
+    bed = tmp_path / "a.junc.bed"
+    bed.write_text("chr1\t100\t120\tj\t50\t+\n")                       # too short: filtered out
+    man = tmp_path / "m.txt"
+    man.write_text(f"s0\t{bed}\tm\tc\ns1\t{bed}\tm\tc\n")
+    quant.run_with(_args(quant, ["-m", str(man), "-o", str(tmp_path / "e")]))
+    assert open(tmp_path / "e_allClusters.tsv").read() == ""
+    assert open(tmp_path / "e_junctions.bed").read() == ""
+    assert open(tmp_path / "e_inclusionCounts.tsv").read() == "cluster\ts0\ts1\n"
+    assert open(tmp_path / "e_allPS.tsv").read() == "cluster\ts0\ts1\n"
+    # one sample -> no pairs: the reference writes "clusterID\t" and "event\t" lines
+    counts = tmp_path / "c.tsv"
+    counts.write_text("cluster\ts0\nchr1:1-100:+\t5\nchr1:50-200:+\t7\n")
+    clusters = tmp_path / "l.tsv"
+    clusters.write_text("chr1:1-100:+\tchr1:50-200:+\nchr1:50-200:+\tchr1:1-100:+\n")
+    out = tmp_path / "p.tsv"
+    pairwise_fisher.run_with(_args(pairwise_fisher, ["--inclusionSPLICEDICE", str(counts), "-c", str(clusters),
+                                                     "-o", str(out)]))
+    assert out.read_text() == "clusterID\t\nchr1:1-100:+\t\nchr1:50-200:+\t\n"
