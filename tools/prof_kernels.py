@@ -43,13 +43,16 @@ def main():
         pa, pb = ops.all_pairs(S)
         out = torch.empty((J, len(pa)), dtype=torch.float64, device=dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        for i in range(3):
+        reps = int(os.environ.get("SD_PROF_REPS", "2"))
+        for _ in range(int(os.environ.get("SD_PROF_WARM", "0"))):       # let the clocks settle before timing
+            ops.fisher_pairwise(inc, exc, pa, pb, out=out)
+        for i in range(1 + reps):
             if i == 1:
                 e0.record()
             ops.fisher_pairwise(inc, exc, pa, pb, out=out)
         e1.record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / 2
+        ms = e0.elapsed_time(e1) / reps
         print(f"fisher {J}x{len(pa)}: {ms:.3f} ms/launch, {J * len(pa) / (ms * 1e-3):.3e} tests/s")
 
 
