@@ -350,15 +350,36 @@ def main():
     for _ in range(args.warmup):
         step()
     barrier()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    # The K timed steps are captured into one CUDA graph, so a busy host cannot open gaps between
+    # the launches (each step is still its own kernel launch inside the graph).  If capture is not
+    # possible the steps are launched one by one.
+    graph = None
+    try:
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                for _ in range(args.steps):
+                    step()
+        torch.cuda.current_stream().wait_stream(side)
+        graph = g
+    except Exception as exc_capture:            # noqa: BLE001 - any capture failure falls back to plain launches
+        print(f"[bench] CUDA-graph capture unavailable ({exc_capture}); launching step by step", file=sys.stderr)
+        torch.cuda.synchronize()
+    e_begin, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    ev[0].record()
-    for i in range(args.steps):
-        step()
-        ev[i + 1].record()
+    e_begin.record()
+    if graph is not None:
+        graph.replay()
+    else:
+        for _ in range(args.steps):
+            step()
+    e_end.record()
     barrier()
-    per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
-    total_ms = max_over_ranks(ev[0].elapsed_time(ev[-1]))
+    total_ms_rank = e_begin.elapsed_time(e_end)
+    per_launch_ms = [total_ms_rank / args.steps]
+    total_ms = max_over_ranks(total_ms_rank)
     cells_total = sum_over_ranks(float(cells_rank))
     ms_per_step = total_ms / args.steps
     value = cells_total / (ms_per_step * 1e-3)
@@ -507,7 +528,8 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "kernel": "quant_wide_kernel<2, true>", "kernel_ms": kernel_ms,
                          "bytes_per_cell": 8, "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks, "fisher": fisher,
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps, "launch_mode": "cuda graph of K kernel launches" if graph is not None else "K stream launches",
+            "clocks": clocks, "fisher": fisher,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

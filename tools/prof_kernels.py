@@ -42,17 +42,18 @@ def main():
         exc = ops.quant_ps(inc, cl["row_ptr"], cl["col_idx"], want_f32=False, want_exc=True)["exc"]
         pa, pb = ops.all_pairs(S)
         out = torch.empty((J, len(pa)), dtype=torch.float64, device=dev)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = int(os.environ.get("SD_PROF_REPS", "2"))
-        for _ in range(int(os.environ.get("SD_PROF_WARM", "0"))):       # let the clocks settle before timing
+        for _ in range(int(os.environ.get("SD_PROF_WARM", "1"))):       # let the clocks settle before timing
             ops.fisher_pairwise(inc, exc, pa, pb, out=out)
-        for i in range(1 + reps):
-            if i == 1:
-                e0.record()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+        ev[0].record()
+        for i in range(reps):
             ops.fisher_pairwise(inc, exc, pa, pb, out=out)
-        e1.record()
+            ev[i + 1].record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / reps
+        per = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(reps))
+        ms = per[len(per) // 2]                   # median: each call has one host round trip
+        print(f"  per-call ms: min {per[0]:.3f} median {ms:.3f} max {per[-1]:.3f}")
         print(f"fisher {J}x{len(pa)}: {ms:.3f} ms/launch, {J * len(pa) / (ms * 1e-3):.3e} tests/s")
 
 
