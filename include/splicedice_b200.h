@@ -147,6 +147,16 @@ int sd_fisher_pairwise(int64_t n_junctions, int32_t n_samples,
                        int64_t n_pairs, const int32_t *pair_a, const int32_t *pair_b,
                        double *p_out, int64_t ld_p,
                        int64_t row_begin, int64_t row_end, void *stream);
+/* Fully asynchronous form: the caller promises 0 <= inc[j,s] + exc[j,s] <= max_cell_bound for every
+ * cell of the row range (a host that filled the matrices knows it), so no reduction and no
+ * stream synchronisation is needed (the table upload synchronises only the first time a larger
+ * table is required).  A table with an entry outside the promise yields NaN, never a wrong p. */
+int sd_fisher_pairwise_bounded(int64_t n_junctions, int32_t n_samples,
+                               const int32_t *inc, int64_t ld_inc,
+                               const int64_t *exc, int64_t ld_exc,
+                               int64_t n_pairs, const int32_t *pair_a, const int32_t *pair_b,
+                               double *p_out, int64_t ld_p,
+                               int64_t row_begin, int64_t row_end, int64_t max_cell_bound, void *stream);
 /* Host-buffer form (the call a ctypes user makes): every pointer is a HOST pointer; row blocks
  * of p-values are computed on one stream while the previous block is copied back on another.
  * Returns when p_out is complete. */

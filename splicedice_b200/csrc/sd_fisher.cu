@@ -80,6 +80,7 @@ struct FisherParams {
     const double2 *table;
     int64_t table_entries;
     int32_t smem_entries;
+    int64_t cell_bound;      // caller-promised (or measured) upper bound on inc + exc; entries outside [0, bound] give NaN
 };
 
 __device__ __forceinline__ void stage_table(double2 *s_tab, const double2 *g_tab, int n)
@@ -110,9 +111,13 @@ __global__ void __launch_bounds__(kFisherThreads, 3) fisher_pairwise_kernel(cons
             const int sa = __ldg(p.pair_a + k), sb = __ldg(p.pair_b + k);
             const int32_t *inc = p.inc + j * p.ld_inc;
             const int64_t *exc = p.exc + j * p.ld_exc;
-            const Int a = (Int)__ldg(inc + sa), b = (Int)__ldg(inc + sb);
-            const Int c = (Int)__ldg(exc + sa), d = (Int)__ldg(exc + sb);
-            __stcs(p.p_out + j * p.ld_p + k, fisher::two_sided<Int>(tab, a, b, c, d));
+            const int64_t a64 = __ldg(inc + sa), b64 = __ldg(inc + sb), c64 = __ldg(exc + sa), d64 = __ldg(exc + sb);
+            double pv;
+            if (a64 < 0 || b64 < 0 || c64 < 0 || d64 < 0 || a64 + c64 > p.cell_bound || b64 + d64 > p.cell_bound)
+                pv = __longlong_as_double(0x7FF8000000000000ll);
+            else
+                pv = fisher::two_sided<Int>(tab, (Int)a64, (Int)b64, (Int)c64, (Int)d64);
+            __stcs(p.p_out + j * p.ld_p + k, pv);
         }
         j += dj;
         t += dt;
@@ -197,8 +202,13 @@ __global__ void __launch_bounds__(kFisherThreads, 3) fisher_pairwise_binned_kern
                 const int64_t k = k0 + s_perm[slot];
                 const int sa = __ldg(p.pair_a + k), sb = __ldg(p.pair_b + k);
                 const int32_t a = __ldg(inc + sa), b = __ldg(inc + sb);
-                const int32_t c = (int32_t)__ldg(exc + sa), d = (int32_t)__ldg(exc + sb);
-                p.p_out[j * p.ld_p + k] = fisher::two_sided<int32_t>(tab, a, b, c, d);
+                const int64_t c64 = __ldg(exc + sa), d64 = __ldg(exc + sb);
+                double pv;
+                if (a < 0 || b < 0 || c64 < 0 || d64 < 0 || a + c64 > p.cell_bound || b + d64 > p.cell_bound)
+                    pv = __longlong_as_double(0x7FF8000000000000ll);      // outside the promised range: loud, not wrong
+                else
+                    pv = fisher::two_sided<int32_t>(tab, a, b, (int32_t)c64, (int32_t)d64);
+                p.p_out[j * p.ld_p + k] = pv;
             }
         }
         __syncthreads();                        // s_perm / s_hist are rebuilt by the next item
@@ -409,6 +419,7 @@ int launch_fisher_pairwise(FisherParams p, cudaStream_t stream, int64_t max_cell
     if (max_cell < 0)
         if (int rc = fisher_max_cell(p, stream, &max_cell)) return rc;
     const int64_t max_total = 2 * max_cell;
+    p.cell_bound = max_cell;
     if (int rc = device_table(max_total + 1, &p.table, &p.table_entries, stream)) return rc;
     p.smem_entries = (int32_t)std::min<int64_t>(std::min<int64_t>(max_total + 1, p.table_entries), kSmemEntriesMax);
     return dispatch<PairwiseLauncher>(max_total, p.smem_entries, p.table_entries, p, stream);
@@ -435,6 +446,26 @@ int sd_fisher_pairwise(int64_t n_junctions, int32_t n_samples, const int32_t *in
     p.n_pairs = n_pairs; p.pair_a = pair_a; p.pair_b = pair_b;
     p.p_out = p_out; p.ld_p = ld_p; p.row_begin = row_begin; p.row_end = row_end;
     return sd::launch_fisher_pairwise(p, (cudaStream_t)stream, -1);
+}
+
+int sd_fisher_pairwise_bounded(int64_t n_junctions, int32_t n_samples, const int32_t *inc, int64_t ld_inc,
+                               const int64_t *exc, int64_t ld_exc, int64_t n_pairs, const int32_t *pair_a,
+                               const int32_t *pair_b, double *p_out, int64_t ld_p, int64_t row_begin,
+                               int64_t row_end, int64_t max_cell_bound, void *stream)
+{
+    SD_REQUIRE(n_junctions >= 0 && n_samples >= 0 && n_pairs >= 0, "sd_fisher_pairwise_bounded: negative size");
+    SD_REQUIRE(row_begin >= 0 && row_begin <= row_end && row_end <= n_junctions,
+               "sd_fisher_pairwise_bounded: row range outside [0, n_junctions)");
+    SD_REQUIRE(max_cell_bound >= 0 && max_cell_bound < (int64_t(1) << 61), "sd_fisher_pairwise_bounded: bad bound");
+    if (row_begin == row_end || n_pairs == 0) return SD_OK;
+    SD_REQUIRE(inc && exc && pair_a && pair_b && p_out, "sd_fisher_pairwise_bounded: null pointer");
+    SD_REQUIRE(ld_inc >= n_samples && ld_exc >= n_samples && ld_p >= n_pairs, "sd_fisher_pairwise_bounded: ld too small");
+    sd::FisherParams p{};
+    p.n_junctions = n_junctions; p.n_samples = n_samples;
+    p.inc = inc; p.ld_inc = ld_inc; p.exc = exc; p.ld_exc = ld_exc;
+    p.n_pairs = n_pairs; p.pair_a = pair_a; p.pair_b = pair_b;
+    p.p_out = p_out; p.ld_p = ld_p; p.row_begin = row_begin; p.row_end = row_end;
+    return sd::launch_fisher_pairwise(p, (cudaStream_t)stream, max_cell_bound);
 }
 
 int sd_fisher_tables(int64_t n_tables, const int64_t *a, const int64_t *b, const int64_t *c,

@@ -52,6 +52,8 @@ _SIGNATURES = {
     "sd_quant_ps_host": (c_int, [c_int, c_int64, c_int32, _P, c_int64, _P, _P, _P, c_int64, _P, c_int64]),
     "sd_fisher_pairwise": (c_int, [c_int64, c_int32, _P, c_int64, _P, c_int64, c_int64, _P, _P,
                                    _P, c_int64, c_int64, c_int64, _P]),
+    "sd_fisher_pairwise_bounded": (c_int, [c_int64, c_int32, _P, c_int64, _P, c_int64, c_int64, _P, _P,
+                                           _P, c_int64, c_int64, c_int64, c_int64, _P]),
     "sd_fisher_tables": (c_int, [c_int64, _P, _P, _P, _P, _P, _P]),
     "sd_fisher_pairwise_host": (c_int, [c_int, c_int64, c_int32, _P, c_int64, _P, c_int64,
                                         c_int64, _P, _P, _P, c_int64]),

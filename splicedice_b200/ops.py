@@ -150,23 +150,34 @@ def all_pairs(n_samples: int):
     return a.astype(np.int32), b.astype(np.int32)
 
 
-def fisher_pairwise(inc, exc, pair_a, pair_b, row_begin=0, row_end=None, out=None):
-    """p[j, k] for tables [[inc[j,a_k], inc[j,b_k]], [exc[j,a_k], exc[j,b_k]]] (sd_fisher_pairwise)."""
+def fisher_pairwise(inc, exc, pair_a, pair_b, row_begin=0, row_end=None, out=None, max_cell_bound=None):
+    """p[j, k] for tables [[inc[j,a_k], inc[j,b_k]], [exc[j,a_k], exc[j,b_k]]] (sd_fisher_pairwise).
+    With ``max_cell_bound`` (an upper bound on inc + exc the caller vouches for) the call is fully
+    asynchronous (sd_fisher_pairwise_bounded); cells outside the bound give NaN."""
     require_cuda()
     if inc.dtype != torch.int32 or exc.dtype != torch.int64 or not inc.is_cuda or not exc.is_cuda:
         raise TypeError("fisher_pairwise: inc int32 / exc int64 CUDA tensors expected")
     J, S = inc.shape
     dev = inc.device
+    # pairs given on the host are validated there; device tensors are trusted (no sync)
+    for arr in (pair_a, pair_b):
+        if not isinstance(arr, torch.Tensor):
+            h = np.asarray(arr)
+            if h.size and (h.min() < 0 or h.max() >= S):
+                raise ValueError("fisher_pairwise: pair index out of range")
     pa, pb = _i32(pair_a, dev), _i32(pair_b, dev)
     P = int(pa.numel())
-    if P and (int(pa.max()) >= S or int(pb.max()) >= S or int(pa.min()) < 0 or int(pb.min()) < 0):
-        raise ValueError("fisher_pairwise: pair index out of range")
     row_end = J if row_end is None else row_end
     if out is None:
         out = torch.empty((J, P), dtype=torch.float64, device=dev)
     with torch.cuda.device(dev):
-        native.call("sd_fisher_pairwise", J, S, native.ptr(inc), inc.stride(0), native.ptr(exc), exc.stride(0),
-                    P, native.ptr(pa), native.ptr(pb), native.ptr(out), out.stride(0), row_begin, row_end, _sp())
+        if max_cell_bound is None:
+            native.call("sd_fisher_pairwise", J, S, native.ptr(inc), inc.stride(0), native.ptr(exc), exc.stride(0),
+                        P, native.ptr(pa), native.ptr(pb), native.ptr(out), out.stride(0), row_begin, row_end, _sp())
+        else:
+            native.call("sd_fisher_pairwise_bounded", J, S, native.ptr(inc), inc.stride(0), native.ptr(exc),
+                        exc.stride(0), P, native.ptr(pa), native.ptr(pb), native.ptr(out), out.stride(0), row_begin,
+                        row_end, int(max_cell_bound), _sp())
     return out
 
 

@@ -82,7 +82,9 @@ def pairwise_pvalues(events, counts, clusters, device=0):
     exc = ops.quant_ps(inc, row_ptr, col_idx, want_f32=False, want_exc=True)["exc"]
     pa = np.array([a for a, _ in pairs], dtype=np.int32)
     pb = np.array([b for _, b in pairs], dtype=np.int32)
-    return ops.fisher_pairwise(inc, exc, pa, pb).cpu().numpy()
+    # the host filled the matrix, so it can vouch for a bound on inc + exc: no reduction / sync on the device
+    bound = int(as_int.max(initial=0)) * (1 + int(np.diff(row_ptr).max(initial=0)))
+    return ops.fisher_pairwise(inc, exc, pa, pb, max_cell_bound=bound).cpu().numpy()
 
 
 def add_parser(parser):

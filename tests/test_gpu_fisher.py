@@ -103,3 +103,26 @@ def test_survey_vector_pairwise_file(golden_dir):
     by_name = {r[0]: i for i, r in enumerate(rows[1:])}
     order = [by_name[n] for n in names]
     np.testing.assert_allclose(got, want[order], rtol=RTOL, atol=0)
+
+
+def test_bounded_entry_point_matches_and_guards():
+    """sd_fisher_pairwise_bounded: same p-values without the device-side reduction; a cell outside
+    the promised bound yields NaN for the tables that use it, never a wrong number."""
+    _, ops = _ops()
+    J, S = 1500, 10
+    _, csr, counts = util.synthetic_problem(J, S, seed=21, zero_frac=0.1)
+    exc = oracle_np.exclusion_sums(counts, csr["row_ptr"], csr["col_idx"])
+    pa, pb = oracle_np.all_pairs(S)
+    dev = torch.device("cuda", 0)
+    inc_d, exc_d = torch.from_numpy(counts).to(dev), torch.from_numpy(exc).to(dev)
+    ref = ops.fisher_pairwise(inc_d, exc_d, pa, pb).cpu().numpy()
+    bound = int((counts + exc).max())
+    got = ops.fisher_pairwise(inc_d, exc_d, pa, pb, max_cell_bound=bound).cpu().numpy()
+    np.testing.assert_array_equal(got, ref)
+    loose = ops.fisher_pairwise(inc_d, exc_d, pa, pb, max_cell_bound=bound * 50).cpu().numpy()   # other instantiation
+    _check(loose.ravel(), ref.ravel(), rtol=1e-12)
+    tight = ops.fisher_pairwise(inc_d, exc_d, pa, pb, max_cell_bound=bound // 2).cpu().numpy()
+    over = (counts + exc) > bound // 2
+    bad = over[:, pa] | over[:, pb]
+    assert bad.any() and np.isnan(tight[bad]).all()
+    np.testing.assert_array_equal(tight[~bad], ref[~bad])
