@@ -64,3 +64,30 @@ def test_empty_set():
     z = np.zeros(0, dtype=np.int32)
     got = ops.cluster_build(z, z, z, z)
     assert got["nnz"] == 0 and got["n_comp"] == 0 and got["row_ptr"].cpu().numpy().tolist() == [0]
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_interval_sets(seed):
+    """Touching, nested and duplicate-start intervals on several chromosomes / strands, sizes 1..3000:
+    device CSR == oracle CSR (list order, components, row order)."""
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(1, 3000))
+    chroms = ["chr1", "chr10", "chr2", "chrX", "GL000219.1"]
+    out = set()
+    while len(out) < n:
+        a = int(rng.integers(0, 5 * n))
+        kind = int(rng.integers(0, 4))
+        length = [int(rng.integers(1, 40)), int(rng.integers(40, 3000)), 50, int(rng.integers(1, 5))][kind]
+        out.add((chroms[int(rng.integers(0, len(chroms)))], a, a + length, "+-"[int(rng.integers(0, 2))]))
+    js = sorted(out)
+    rng.shuffle(js)
+    arrays = oracle_np.junctions_to_arrays(js)[:4]
+    _compare(arrays)
+
+
+def test_one_giant_component():
+    """A junction spanning everything: every other junction is its neighbour (degree J - 1)."""
+    js = [("chr1", 0, 10_000_000, "+")] + [("chr1", 100 * i + 10, 100 * i + 60, "+") for i in range(20000)]
+    arrays = oracle_np.junctions_to_arrays(js)[:4]
+    got, want = _compare(arrays)
+    assert got["n_comp"] == 1 and got["nnz"] == 2 * 20000

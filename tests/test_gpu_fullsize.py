@@ -80,3 +80,32 @@ def test_pairwise_fisher_full_size():
     got = p[sel].cpu().numpy()
     ok = want > 1e-300
     assert (np.abs(got[ok] - want[ok]) / want[ok]).max() < 1e-11
+
+
+def test_ir_ratio_full_size():
+    """configs[4]: intron-retention ratio from precomputed coverage, 1,000 samples x 400,000 junctions."""
+    from splicedice_b200 import ops, synth
+    ops.require_cuda()
+    dev = torch.device("cuda", 0)
+    J, S = 400_000, 1000
+    cl = ops.cluster_build(*synth.junction_arrays(J, 79)[:4])
+    rp, ci = cl["row_ptr"].cpu().numpy(), cl["col_idx"].cpu().numpy()
+    counts = ops.synth_counts(6, 0, J, S, device=dev)
+    med = (ops.synth_counts(7, 0, J, S, p=0.2, device=dev) % 9).double()          # coverage medians 0..8
+    ir = ops.ir_ratio(med, counts, cl["row_ptr"], cl["col_idx"])
+    torch.cuda.synchronize()
+    rows = np.sort(np.random.default_rng(2).choice(J, 120, replace=False))
+    need = sorted(set(rows.tolist()) | {int(c) for r in rows for c in ci[rp[r]:rp[r + 1]]})
+    at = {r: k for k, r in enumerate(need)}
+    host = synth.counts_host(6, 0, len(need), S, rows=need, ld_cols=S).astype(np.int64)
+    med_h = (synth.counts_host(7, 0, len(rows), S, p=0.2, rows=rows, ld_cols=S) % 9).astype(np.float64)
+    got = ir[torch.from_numpy(rows).to(dev)].cpu().numpy()
+    for k, r in enumerate(rows):
+        total = host[at[int(r)]] + (host[[at[int(c)] for c in ci[rp[r]:rp[r + 1]]]].sum(axis=0) if rp[r + 1] > rp[r] else 0)
+        den = med_h[k] + total
+        with np.errstate(divide="ignore", invalid="ignore"):
+            want = np.where(den == 0, np.nan, med_h[k] / den)
+        np.testing.assert_array_equal(np.isnan(got[k]), np.isnan(want))
+        np.testing.assert_array_equal(got[k][~np.isnan(want)], want[~np.isnan(want)])
+    finite = ~torch.isnan(ir)
+    assert bool(((ir[finite] >= 0) & (ir[finite] <= 1)).all())
