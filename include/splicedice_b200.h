@@ -169,6 +169,23 @@ int sd_fisher_pairwise_host(int device, int64_t n_junctions, int32_t n_samples,
 int sd_fisher_tables(int64_t n_tables, const int64_t *a, const int64_t *b,
                      const int64_t *c, const int64_t *d, double *p_out, void *stream);
 
+/* ---- Benjamini-Hochberg adjustment of the p-value matrix (device) ---------------------------
+ * Replaces the multiple-test correction of pairwise_fisher.run_with (pairwise_fisher.py:182-191):
+ * statsmodels multipletests(method="fdr_bh")[1] applied to every column ("pairwise", the CLI
+ * default; SD_BH_COLUMNS) or to the flattened matrix ("all"; SD_BH_ALL).  For the n values of a
+ * segment sorted ascending,  adj_(k) = min(1, min_{m >= k} p_(m) / (m / n))  with both divisions
+ * in IEEE binary64, so results are bit-identical to the numpy expression statsmodels evaluates.
+ * p / out: DEVICE matrices [n_rows, n_cols] (out may alias p); at most 2^31 - 1 values per call
+ * (SD_ERR_UNSUPPORTED beyond: column blocks are independent, split them).  Asynchronous on
+ * `stream`; scratch comes from a caller-provided device workspace (~25 bytes per value).
+ */
+#define SD_BH_COLUMNS 0
+#define SD_BH_ALL 1
+size_t sd_bh_workspace_bytes(int64_t n_rows, int64_t n_cols, int mode);
+int sd_bh_adjust(int64_t n_rows, int64_t n_cols, const double *p, int64_t ld_p,
+                 double *out, int64_t ld_out, int mode,
+                 void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---- K4: intron-retention ratio ----------------------------------------------------
  * Replaces the arithmetic of ir_table.calculateIR (ir_table.py:118-132):
  *   ir[r,s] = median[r,s] / (median[r,s] + inc[r,s] + sum_{c in adj(r)} inc[c,s]),  x/0 -> NaN

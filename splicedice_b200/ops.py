@@ -196,6 +196,47 @@ def fisher_pairwise_host(inc, exc, pair_a, pair_b, out=None, device=0):
     return out
 
 
+BH_COLUMNS, BH_ALL = 0, 1
+_BH_MAX_VALUES = 2 ** 31 - 1
+
+
+def bh_adjust(p, mode="pairwise", out=None):
+    """Benjamini-Hochberg adjusted p-values of a CUDA float64 matrix [rows, cols] (sd_bh_adjust):
+    ``mode='pairwise'`` adjusts every column on its own, ``'all'`` the flattened matrix
+    (pairwise_fisher.py:182-191).  ``out`` may be ``p`` itself.  Column mode splits into column
+    blocks when the matrix holds more than 2^31 - 1 values."""
+    require_cuda()
+    if p.dtype != torch.float64 or not p.is_cuda or p.dim() != 2 or (p.numel() and p.stride(1) != 1):
+        raise TypeError("bh_adjust: a 2-D float64 CUDA tensor with unit column stride expected")
+    if mode not in ("pairwise", "all"):
+        raise ValueError("bh_adjust: mode must be 'pairwise' or 'all'")
+    if out is None:
+        out = torch.empty_like(p)
+    rows, cols = p.shape
+    if rows == 0 or cols == 0:
+        return out
+    kind = BH_COLUMNS if mode == "pairwise" else BH_ALL
+    if rows * cols > _BH_MAX_VALUES:
+        if kind == BH_ALL or rows > _BH_MAX_VALUES:
+            raise ValueError("bh_adjust: more than 2^31 - 1 values in one segment")
+        step = _BH_MAX_VALUES // rows
+    else:
+        step = cols
+    with torch.cuda.device(p.device):
+        ws = None
+        for c0 in range(0, cols, step):
+            c1 = min(cols, c0 + step)
+            need = native.load().sd_bh_workspace_bytes(rows, c1 - c0, kind)
+            if need == 0:
+                raise native.NativeCallError("sd_bh_workspace_bytes", 1, native.last_error())
+            if ws is None or ws.numel() < need:
+                ws = torch.empty(need, dtype=torch.uint8, device=p.device)
+            src, dst = p[:, c0:c1], out[:, c0:c1]
+            native.call("sd_bh_adjust", rows, c1 - c0, native.ptr(src), p.stride(0), native.ptr(dst), out.stride(0),
+                        kind, native.ptr(ws), ws.numel(), _sp())
+    return out
+
+
 def fisher_tables(a, b, c, d, device=None):
     """Element-wise two-sided p of [[a, b], [c, d]] (sd_fisher_tables)."""
     dev = _dev(device)

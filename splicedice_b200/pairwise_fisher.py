@@ -3,8 +3,9 @@
 Host mirror of /root/reference/splicedice/pairwise_fisher.py (same flags, inputs and output
 file).  The hot loop (pairwise_fisher.py:154-180) runs on the GPU: exclusion counts with
 sd_quant_ps over the cluster CSR, then sd_fisher_pairwise for the [events x pairs] p-values.
-Benjamini-Hochberg and the writer stay on the host.  ``--chi2`` is not implemented (out of
-scope: BASELINE.json names the Fisher path only) and is rejected loudly.
+Benjamini-Hochberg runs on the device too (sd_bh_adjust); the writer is the native host
+formatter.  ``--chi2`` is not implemented (out of scope: BASELINE.json names the Fisher path
+only) and is rejected loudly.
 """
 from __future__ import annotations
 
@@ -40,28 +41,27 @@ def getEventCounts(filename, filter_list=None):
     return samples, events, counts
 
 
-def fdr_bh(p):
-    """Benjamini-Hochberg adjusted p-values (statsmodels multipletests(method='fdr_bh')[1])."""
-    p = np.asarray(p, dtype=np.float64)
-    n = p.size
-    if n == 0:
+def fdr_bh(p, device=0):
+    """Benjamini-Hochberg adjusted p-values of a 1-D array, as statsmodels
+    multipletests(method='fdr_bh')[1] (pairwise_fisher.py:185,190), computed on the GPU
+    (sd_bh_adjust: radix sort, p / (rank / n), running minimum from the right, clip at 1)."""
+    from . import ops
+    import torch
+    p = np.ascontiguousarray(p, dtype=np.float64).reshape(-1)
+    if p.size == 0:
         return p.copy()
-    order = np.argsort(p, kind="stable")
-    scaled = p[order] / (np.arange(1, n + 1, dtype=np.float64) / float(n))
-    scaled = np.minimum.accumulate(scaled[::-1])[::-1]
-    scaled[scaled > 1] = 1
-    out = np.empty(n, dtype=np.float64)
-    out[order] = scaled
-    return out
+    d = torch.from_numpy(p).to(torch.device("cuda", device)).reshape(-1, 1)
+    return ops.bh_adjust(d, "all", out=d).reshape(-1).cpu().numpy()
 
 
 def sample_pairs(n_samples):
     return [(i, j) for i in range(n_samples - 1) for j in range(i + 1, n_samples)]
 
 
-def pairwise_pvalues(events, counts, clusters, device=0):
-    """float64[len(events), n_pairs] two-sided Fisher p-values (uncorrected), pair order as
-    ``sample_pairs``."""
+def pairwise_pvalues(events, counts, clusters, device=0, correction="none"):
+    """float64[len(events), n_pairs] two-sided Fisher p-values, pair order as ``sample_pairs``;
+    ``correction`` = 'none' | 'pairwise' | 'all' applies Benjamini-Hochberg on the device before
+    the matrix comes back (pairwise_fisher.py:182-191)."""
     from . import ops
     import torch
     n_events, n_samples = counts.shape if counts.ndim == 2 else (0, 0)
@@ -84,7 +84,10 @@ def pairwise_pvalues(events, counts, clusters, device=0):
     pb = np.array([b for _, b in pairs], dtype=np.int32)
     # the host filled the matrix, so it can vouch for a bound on inc + exc: no reduction / sync on the device
     bound = int(as_int.max(initial=0)) * (1 + int(np.diff(row_ptr).max(initial=0)))
-    return ops.fisher_pairwise(inc, exc, pa, pb, max_cell_bound=bound).cpu().numpy()
+    p = ops.fisher_pairwise(inc, exc, pa, pb, max_cell_bound=bound)
+    if correction != "none":
+        ops.bh_adjust(p, correction, out=p)
+    return p.cpu().numpy()
 
 
 def add_parser(parser):
@@ -115,13 +118,9 @@ def run_with(args):
     columns = [f"{samples[a]}_{samples[b]}" for a, b in pairs]
     print("Analyzing pairs:")
     print(",".join(columns))
-    parray = pairwise_pvalues(events, counts, clusters, getattr(args, "device", 0))
+    parray = pairwise_pvalues(events, counts, clusters, getattr(args, "device", 0),
+                              correction=args.multiple_test_correction)
     print(f"[{len(events)} / {len(events)}] events analyzed...")
-    if args.multiple_test_correction == "all":
-        parray = fdr_bh(parray.ravel()).reshape(parray.shape)
-    elif args.multiple_test_correction == "pairwise":
-        for k in range(parray.shape[1]):
-            parray[:, k] = fdr_bh(parray[:, k])
     from . import textio
     textio.write_matrix(args.output, "clusterID\t" + "\t".join(columns) + "\n", events,
                         np.ascontiguousarray(parray, dtype=np.float64), repr_floats=True)
