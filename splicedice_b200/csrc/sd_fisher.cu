@@ -81,6 +81,7 @@ struct FisherParams {
     int64_t table_entries;
     int32_t smem_entries;
     int64_t cell_bound;      // caller-promised (or measured) upper bound on inc + exc; entries outside [0, bound] give NaN
+    bool binned;             // cost-binned kernel (every table total below 2^30)
 };
 
 __device__ __forceinline__ void stage_table(double2 *s_tab, const double2 *g_tab, int n)
@@ -137,33 +138,74 @@ __global__ void __launch_bounds__(kFisherThreads, 3) fisher_pairwise_kernel(cons
 constexpr int kBinChunk = 2048;
 constexpr int kBinBuckets = 64;
 
-__device__ __forceinline__ int cost_bucket(int a, int b, long long c64, long long d64)
+// Only the ORDER of the pairs depends on this key, so it uses the approximate SFU forms
+// (MUFU.RCP / RSQ / LG2) throughout: ~45 instructions per pair.
+__device__ __forceinline__ int cost_bucket(int a, int b, int c, int d)
 {
-    const float fa = (float)a, fb = (float)b, fc = (float)c64, fd = (float)d64;
+    const float fa = (float)a, fb = (float)b, fc = (float)c, fd = (float)d;
     const float n1 = fa + fb, n2 = fc + fd, n = fa + fc, N = n1 + n2;
     if (n1 == 0.f || n2 == 0.f || n == 0.f || fb + fd == 0.f) return 0;
-    const float mode = floorf((n + 1.f) * (n1 + 1.f) / (N + 2.f));
-    const float var = n * (n1 / N) * (n2 / N) * ((N - n) / fmaxf(N - 1.f, 1.f));
-    const float sig = sqrtf(fmaxf(var, 1e-6f));
-    const float z = fabsf(fa - mode) / sig;
-    const float terms = sig * (sqrtf(z * z + 66.5f) - z);
-    return min(kBinBuckets - 1, 1 + (int)(6.0f * log2f(1.0f + terms)));
+    const float rN = __fdividef(1.f, N);
+    const float mode = floorf((n + 1.f) * (n1 + 1.f) * __fdividef(1.f, N + 2.f));
+    const float var = fmaxf((n * rN) * (n1 * rN) * (n2 * (N - n)) * __fdividef(1.f, fmaxf(N - 1.f, 1.f)), 1e-6f);
+    const float inv_sig = rsqrtf(var);
+    const float z = fabsf(fa - mode) * inv_sig;
+    const float t = fmaf(z, z, 66.5f);
+    const float terms = var * inv_sig * (t * rsqrtf(t) - z);
+    return min(kBinBuckets - 1, 1 + (int)(6.0f * __log2f(1.0f + terms)));
 }
 
-template <int kMode>
-__global__ void __launch_bounds__(kFisherThreads, 3) fisher_pairwise_binned_kernel(const FisherParams p)
+// kSub independent groups of 256 threads share one CTA (and one copy of the staged table): each
+// group walks its own items and synchronises on its own named barrier, so a 768-thread CTA
+// behaves like three 256-thread CTAs that need a single table in shared memory.
+__device__ __forceinline__ void group_sync(int group)
 {
+    asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(kFisherThreads) : "memory");
+}
+
+// kStaged: the junction's inclusion / exclusion row (n_samples <= kStageSamples) is copied to
+// shared memory once per item as int32 pairs, cells outside [0, cell_bound] marked -1, so both
+// passes over the pairs read it with 32-bit shared addressing instead of 64-bit global gathers.
+constexpr int kStageSamples = 512;
+struct GroupBins {
+    uint16_t perm[kBinChunk], rank[kBinChunk];
+    uint8_t key[kBinChunk];
+    int hist[kBinBuckets], base[kBinBuckets], next, pad[3];
+    int32_t cell[2][kStageSamples];
+};
+static_assert(sizeof(GroupBins) % 16 == 0, "GroupBins must keep 16-byte alignment between groups");
+
+template <int kMode, int kSub, bool kStaged>
+__global__ void __launch_bounds__(kFisherThreads *kSub, 1) fisher_pairwise_binned_kernel(const FisherParams p)
+{
+    // dynamic shared memory: the staged table, then one GroupBins per 256-thread group
     extern __shared__ __align__(16) double2 s_tab[];
-    __shared__ uint16_t s_perm[kBinChunk], s_rank[kBinChunk];
-    __shared__ uint8_t s_key[kBinChunk];
-    __shared__ int s_hist[kBinBuckets], s_base[kBinBuckets], s_next;
     stage_table(s_tab, p.table, p.smem_entries);
     const DeviceTable<kMode> tab{smem_u32(s_tab), p.table, p.smem_entries, p.table_entries};
 
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int group = (int)(threadIdx.x / kFisherThreads);
+    const int tid = (int)(threadIdx.x % kFisherThreads), lane = tid & 31;
+    GroupBins &bins = reinterpret_cast<GroupBins *>(s_tab + p.smem_entries)[group];
+    uint16_t *s_perm = bins.perm, *s_rank = bins.rank;
+    uint8_t *s_key = bins.key;
+    int *s_hist = bins.hist, *s_base = bins.base, *s_next = &bins.next;
+    int32_t *s_inc = bins.cell[0], *s_exc = bins.cell[1];
     const int64_t chunks_per_row = (p.n_pairs + kBinChunk - 1) / kBinChunk;
     const int64_t n_items = (p.row_end - p.row_begin) * chunks_per_row;
-    for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+    // the four cells of pair k of the current junction; a < 0 flags a cell outside the promise
+    auto cells = [&](const int32_t *inc, const int64_t *exc, int64_t k, int &a, int &b, int &c, int &d) {
+        const int sa = __ldg(p.pair_a + k), sb = __ldg(p.pair_b + k);
+        if (kStaged) {
+            a = s_inc[sa] | s_inc[sb]; b = s_inc[sb]; c = s_exc[sa]; d = s_exc[sb];
+            if (a >= 0) a = s_inc[sa];
+        } else {
+            const int32_t ia = __ldg(inc + sa), ib = __ldg(inc + sb);
+            const int64_t ea = __ldg(exc + sa), eb = __ldg(exc + sb);
+            const bool bad = ia < 0 || ib < 0 || ea < 0 || eb < 0 || ia + ea > p.cell_bound || ib + eb > p.cell_bound;
+            a = bad ? -1 : ia; b = ib; c = (int)ea; d = (int)eb;
+        }
+    };
+    for (int64_t item = (int64_t)blockIdx.x * kSub + group; item < n_items; item += (int64_t)gridDim.x * kSub) {
         const int64_t j = p.row_begin + item / chunks_per_row;
         const int64_t k0 = (item % chunks_per_row) * kBinChunk;
         const int cnt = (int)min((int64_t)kBinChunk, p.n_pairs - k0);
@@ -171,47 +213,63 @@ __global__ void __launch_bounds__(kFisherThreads, 3) fisher_pairwise_binned_kern
         const int64_t *exc = p.exc + j * p.ld_exc;
 
         if (tid < kBinBuckets) s_hist[tid] = 0;
-        if (tid == 0) s_next = 0;
-        __syncthreads();
+        if (tid == 0) *s_next = 0;
+        if (kStaged) {
+            for (int sm = tid; sm < p.n_samples; sm += kFisherThreads) {
+                const int32_t ia = __ldg(inc + sm);
+                const int64_t ea = __ldg(exc + sm);
+                const bool bad = ia < 0 || ea < 0 || ia + ea > p.cell_bound;
+                s_inc[sm] = bad ? -1 : ia;
+                s_exc[sm] = bad ? -1 : (int32_t)ea;
+            }
+        }
+        group_sync(group);
         // cost key of each pair and its rank inside the key's bucket
 #pragma unroll 1
         for (int q = tid; q < cnt; q += kFisherThreads) {
-            const int sa = __ldg(p.pair_a + k0 + q), sb = __ldg(p.pair_b + k0 + q);
-            const int key = cost_bucket(__ldg(inc + sa), __ldg(inc + sb), __ldg(exc + sa), __ldg(exc + sb));
+            int a, b, c, d;
+            cells(inc, exc, k0 + q, a, b, c, d);
+            const int key = a < 0 ? 0 : cost_bucket(a, b, c, d);
             s_key[q] = (uint8_t)key;
             s_rank[q] = (uint16_t)atomicAdd(&s_hist[key], 1);
         }
-        __syncthreads();
-        if (tid == 0) {                         // descending key order: the costliest groups start first
-            int run = 0;
-            for (int bkt = kBinBuckets - 1; bkt >= 0; --bkt) { s_base[bkt] = run; run += s_hist[bkt]; }
+        group_sync(group);
+        if (tid < 32) {                         // descending key order: the costliest groups start first
+            const int h1 = s_hist[kBinBuckets - 1 - 2 * tid], h2 = s_hist[kBinBuckets - 2 - 2 * tid];
+            int incl = h1 + h2;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (tid >= o) incl += up;
+            }
+            s_base[kBinBuckets - 1 - 2 * tid] = incl - h1 - h2;
+            s_base[kBinBuckets - 2 - 2 * tid] = incl - h2;
         }
-        __syncthreads();
+        group_sync(group);
 #pragma unroll 1
         for (int q = tid; q < cnt; q += kFisherThreads) s_perm[s_base[s_key[q]] + s_rank[q]] = (uint16_t)q;
-        __syncthreads();
+        group_sync(group);
 
         const int groups = (cnt + 31) / 32;
         for (;;) {
             int g = 0;
-            if (lane == 0) g = atomicAdd(&s_next, 1);
+            if (lane == 0) g = atomicAdd(s_next, 1);
             g = __shfl_sync(0xffffffffu, g, 0);
             if (g >= groups) break;
             const int slot = g * 32 + lane;
             if (slot < cnt) {
                 const int64_t k = k0 + s_perm[slot];
-                const int sa = __ldg(p.pair_a + k), sb = __ldg(p.pair_b + k);
-                const int32_t a = __ldg(inc + sa), b = __ldg(inc + sb);
-                const int64_t c64 = __ldg(exc + sa), d64 = __ldg(exc + sb);
+                int a, b, c, d;
+                cells(inc, exc, k, a, b, c, d);
                 double pv;
-                if (a < 0 || b < 0 || c64 < 0 || d64 < 0 || a + c64 > p.cell_bound || b + d64 > p.cell_bound)
+                if (a < 0)
                     pv = __longlong_as_double(0x7FF8000000000000ll);      // outside the promised range: loud, not wrong
                 else
-                    pv = fisher::two_sided<int32_t>(tab, a, b, (int32_t)c64, (int32_t)d64);
+                    pv = fisher::two_sided<int32_t>(tab, a, b, c, d);
                 p.p_out[j * p.ld_p + k] = pv;
             }
         }
-        __syncthreads();                        // s_perm / s_hist are rebuilt by the next item
+        group_sync(group);                      // s_perm / s_hist / the staged row are rebuilt by the next item
     }
 }
 
@@ -313,6 +371,7 @@ static int device_table(int64_t need, const double2 **table, int64_t *entries, c
 }
 
 constexpr int kSmemEntriesMax = 6144;      // 96 KB of double2: two CTAs per SM
+constexpr int kSmemEntriesBinned = 10240;  // binned kernel: one CTA per SM, 160 KB of table + 60 KB of bins / staged rows
 
 static int scan_result(unsigned long long *d_max, int *d_neg, cudaStream_t stream, int64_t *max_total,
                        const char *who)
@@ -327,10 +386,10 @@ static int scan_result(unsigned long long *d_max, int *d_neg, cudaStream_t strea
     return SD_OK;
 }
 
-static int fisher_grid(const void *kernel, size_t smem)
+static int fisher_grid(const void *kernel, size_t smem, int threads = kFisherThreads)
 {
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kFisherThreads, smem) != cudaSuccess ||
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess ||
         per_sm < 1)
         per_sm = 1;
     int dev = 0, sms = kSMs;
@@ -356,19 +415,27 @@ static int dispatch(int64_t max_total, int64_t smem_entries, int64_t table_entri
 
 template <class Int, int kMode>
 struct PairwiseLauncher {
+    template <int kSub, bool kStaged>
+    static int launch_binned(const FisherParams &p, cudaStream_t stream)
+    {
+        auto kernel = fisher_pairwise_binned_kernel<kMode, kSub, kStaged>;
+        const size_t smem = (size_t)p.smem_entries * sizeof(double2) + kSub * sizeof(GroupBins);
+        SD_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)(kSmemEntriesBinned * sizeof(double2) + kSub * sizeof(GroupBins))));
+        const int64_t items = (p.row_end - p.row_begin) * ((p.n_pairs + kBinChunk - 1) / kBinChunk);
+        int grid = fisher_grid((const void *)kernel, smem, kFisherThreads * kSub);
+        grid = (int)std::min<int64_t>(grid, (items + kSub - 1) / kSub);
+        kernel<<<grid, kFisherThreads * kSub, smem, stream>>>(p);
+        return check_launch("fisher_pairwise_binned_kernel");
+    }
     static int run(const FisherParams &p, cudaStream_t stream)
     {
-        if (sizeof(Int) == 4 && !getenv("SD_FISHER_PLAIN")) {
-            // every table total fits 31 bits: the cost-binned kernel
-            auto kernel = fisher_pairwise_binned_kernel<kMode>;
-            const size_t smem = (size_t)p.smem_entries * sizeof(double2);
-            SD_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)(kSmemEntriesMax * sizeof(double2))));
-            const int64_t items = (p.row_end - p.row_begin) * ((p.n_pairs + kBinChunk - 1) / kBinChunk);
-            int grid = fisher_grid((const void *)kernel, smem);
-            grid = (int)std::min<int64_t>(grid, items);
-            kernel<<<grid, kFisherThreads, smem, stream>>>(p);
-            return check_launch("fisher_pairwise_binned_kernel");
+        if (p.binned) {
+            // every table total fits 31 bits: the cost-binned kernel, 4 x 256 threads per SM when the
+            // whole table is staged (64 registers, no spills), 3 x 256 otherwise
+            constexpr int kSub = kMode == 0 ? 4 : 3;
+            return p.n_samples <= kStageSamples ? launch_binned<kSub, true>(p, stream)
+                                                : launch_binned<kSub, false>(p, stream);
         }
         auto kernel = fisher_pairwise_kernel<Int, kMode>;
         const size_t smem = (size_t)p.smem_entries * sizeof(double2);
@@ -420,8 +487,10 @@ int launch_fisher_pairwise(FisherParams p, cudaStream_t stream, int64_t max_cell
         if (int rc = fisher_max_cell(p, stream, &max_cell)) return rc;
     const int64_t max_total = 2 * max_cell;
     p.cell_bound = max_cell;
+    p.binned = max_total < (int64_t(1) << 30) && !getenv("SD_FISHER_PLAIN");
     if (int rc = device_table(max_total + 1, &p.table, &p.table_entries, stream)) return rc;
-    p.smem_entries = (int32_t)std::min<int64_t>(std::min<int64_t>(max_total + 1, p.table_entries), kSmemEntriesMax);
+    p.smem_entries = (int32_t)std::min<int64_t>(std::min<int64_t>(max_total + 1, p.table_entries),
+                                                p.binned ? kSmemEntriesBinned : kSmemEntriesMax);
     return dispatch<PairwiseLauncher>(max_total, p.smem_entries, p.table_entries, p, stream);
 }
 

@@ -26,6 +26,7 @@
 
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #ifdef __CUDACC__
 #define SD_HD __host__ __device__ __forceinline__
@@ -99,6 +100,30 @@ SD_HD double tail_sum(double p, double q, double u, double v)
 // quadratics in k, advanced by second differences: two additions each instead of two additions
 // and a multiplication, 7 FP64 operations per term.  A tail that runs out of support multiplies
 // its term by zero and stops at the next check.
+// high 32 bits of a binary64 (sign, exponent, top 20 fraction bits): for positive values an integer
+// comparison of these words orders the values to within 2^-20 relative
+SD_HD int32_t hi_word(double x)
+{
+#ifdef __CUDA_ARCH__
+    return __double2hiint(x);
+#else
+    int64_t bits;
+    memcpy(&bits, &x, sizeof bits);
+    return (int32_t)(bits >> 32);
+#endif
+}
+// x * 2^-500 for x >= 2^500 (exact): an integer subtraction on the exponent field on the device
+SD_HD double scale_down(double x)
+{
+#ifdef __CUDA_ARCH__
+    return __hiloint2double(__double2hiint(x) - (500 << 20), __double2loint(x));
+#else
+    return x * kSmall;
+#endif
+}
+constexpr int32_t kBigHi = (1023 + 500) << 20;      // hi_word(2^500)
+constexpr int32_t kCutHi = 48 << 20;                // 2^-48 in hi_word units
+
 struct TailState {
     double num, s, den, w, P, Q, A;
     SD_HD void init(double p, double q, double u, double v)
@@ -113,8 +138,14 @@ struct TailState {
         P *= num; Q *= den; A = fma(A, den, P);
         num -= s; s -= 2.0; den += w; w += 2.0;
     }
-    SD_HD bool done() const { return P <= kCut * A; }
-    SD_HD void rescale() { if (Q > kBig) { P *= kSmall; Q *= kSmall; A *= kSmall; } }
+    // The cut and the rescale test compare exponent words with integer instructions (the FP64
+    // pipe is the bottleneck): the tail stops once the term is below 2^-48 (to within the 20
+    // fraction bits of the word) of the running sum; P >= 0, A >= Q >= 1 always.
+    SD_HD bool done() const { return hi_word(P) < hi_word(A) - kCutHi; }
+    SD_HD void rescale()
+    {
+        if (hi_word(Q) >= kBigHi) { P *= kSmall; Q = scale_down(Q); A = scale_down(A); }
+    }
 };
 
 // one tail, relative to its first term
@@ -152,12 +183,13 @@ struct Problem {
     Int n1, n2, n;
     Int a, b, c, d;
     double tol;   // bound on the error of a hi-only evaluation of G(a) - G(x)
+    double Ga;    // G(a) from the hi words, computed once (every probe of the search needs it)
 
-    // f(x) = log(pmf(x) / pmf(a)) from the hi words only
+    // f(x) = log(pmf(x) / pmf(a)) from the hi words only: at most seven roundings of at most
+    // eps/2 * lg[N] each (every partial sum is below lg[N]), well inside `tol`
     SD_HD double f_fast(Int x) const
     {
-        return (tab.hi(a) - tab.hi(x)) + (tab.hi(b) - tab.hi(n1 - x)) + (tab.hi(c) - tab.hi(n - x)) +
-               (tab.hi(d) - tab.hi(n2 - n + x));
+        return Ga - ((tab.hi(x) + tab.hi(n1 - x)) + (tab.hi(n - x) + tab.hi(n2 - n + x)));
     }
     SD_HD dd f_exact(Int x) const { return f_exact_of<Table, Int>(tab, a, b, c, d, n1, n2, n, x); }
     // scipy's far-side admission test: pmf(x) <= pexact * (1 + 1e-14)
@@ -208,8 +240,9 @@ SD_HD Plan<Int> make_plan(const Table &tab, Int a, Int b, Int c, Int d)
     }
     const Int hi = n1 < n ? n1 : n;
 
-    Problem<Table, Int> pr{tab, n1, n2, n, a, b, c, d, 0.0};
+    Problem<Table, Int> pr{tab, n1, n2, n, a, b, c, d, 0.0, 0.0};
     pr.tol = 64.0 * 2.220446049250313e-16 * (tab.hi(N) + 1.0);
+    pr.Ga = (tab.hi(a) + tab.hi(b)) + (tab.hi(c) + tab.hi(d));
 
     // tie between the observed table and the mode (plateau or mirror twin)
     {
