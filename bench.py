@@ -163,7 +163,8 @@ def fisher_work(a, b, c, d):
             big = Q > 2.0 ** 500
             P = np.where(big, P * 2.0 ** -500, P); Q = np.where(big, Q * 2.0 ** -500, Q); A = np.where(big, A * 2.0 ** -500, A)
             count = np.where(done, count, count + 1)
-            done |= P <= 2.0 ** -48 * A
+            # TailState::done(): integer comparison of the exponent words (top 32 bits)
+            done |= (P.view(np.int64) >> 32) < (A.view(np.int64) >> 32) - (48 << 20)
             if done.all():
                 break
         return count
@@ -295,6 +296,9 @@ def main():
     from splicedice_b200 import native, ops, sharding, synth
 
     ops.require_cuda()
+    # host buffers of this rank on the GPU's own NUMA node (matters for the e2e figures at N > 1)
+    from splicedice_b200 import distributed as sd_dist
+    numa_cpus = sd_dist.bind_to_gpu_numa(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -419,7 +423,8 @@ def main():
             raise SystemExit(f"rank {rank}: host-pipeline PS differs from the device-resident PS")
         e2e = {"value": cells_total / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "steps": n_e2e,
                "h2d_bytes_per_step": int(Jr * S * 4 + rp.nbytes + ci.nbytes), "d2h_bytes_per_step": int(Jr * S * 4),
-               "api": "sd_quant_ps_host (pinned host counts -> pinned host PS)"}
+               "api": "sd_quant_ps_host (pinned host counts -> pinned host PS)",
+               "host_cpus_local_to_gpu": len(numa_cpus) if numa_cpus else None}
         del h_counts, h_ps
 
     # ---- pairwise Fisher (configs[2]) ----------------------------------------------------------
@@ -456,14 +461,14 @@ def main():
         tests_total = sum_over_ranks(float(Jfr * len(pa)))
         # work actually done per test: tail terms summed by the kernel's rule
         # (cut at 2^-48 of the running sum, checked every 4 terms) on a sample of rows, 8 flop per
-        # term (4 DADD + 2 DMUL + 1 DFMA) + 400 flop of per-table setup; SURVEY.md 8d's model
+        # term (4 DADD + 2 DMUL + 1 DFMA) + 300 flop of per-table setup; SURVEY.md 8d's model
         # (32 flop per support point) is reported beside it
         sel = np.sort(np.random.default_rng(5).choice(Jfr, size=min(120, Jfr), replace=False))
         inc_h = inc[torch.from_numpy(sel).to(dev)].cpu().numpy().astype(np.float64)
         exc_h = exc[torch.from_numpy(sel).to(dev)].cpu().numpy().astype(np.float64)
         terms, support, trivial = fisher_work(inc_h[:, pa], inc_h[:, pb], exc_h[:, pa], exc_h[:, pb])
         fp64_peak = ops.probe_fp64(dev)
-        flops_per_test = 8.0 * terms + 400.0 * (1.0 - trivial)
+        flops_per_test = 8.0 * terms + 300.0 * (1.0 - trivial)
         tests_per_s = tests_total / (f_ms * 1e-3)
         useful = flops_per_test * tests_per_s / world / 1e12
         fisher = {"metric": "fisher_tests_per_s", "value": tests_per_s, "unit": "tests/s",
@@ -473,16 +478,35 @@ def main():
                              "mean_tail_terms_summed": terms},
                   "roofline": {"bound": "fp64", "achieved": useful, "peak": fp64_peak / 1e3, "unit": "TFLOP/s",
                                "frac": useful / (fp64_peak / 1e3), "flops_per_test": flops_per_test,
-                               "model": "8 flop per summed tail term + 400 flop per non-trivial table (per GPU); the FP64 "
+                               "model": "8 flop per summed tail term + 300 flop per non-trivial table (per GPU); the FP64 "
                                         "pipe issues DADD/DMUL at the DFMA rate and divergent lanes idle, so pipe "
                                         "occupancy (ncu) is the utilisation figure",
                                "pipe_fp64_active_ncu": fisher_pipe_active(),
                                "survey_model_tflops": 32.0 * support * tests_per_s / world / 1e12,
                                "peak_source": "sd_probe_fp64 (FMA microbenchmark, same run)"},
                   "dtype": "f64", "gpu_launches": n_f}
+        # Benjamini-Hochberg per column on the same matrix (the CLI's default correction), device-resident
+        try:
+            padj = torch.empty_like(pout)
+            ops.bh_adjust(pout, "pairwise", out=padj)
+            barrier()
+            bev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            bev[0].record()
+            for i in range(3):
+                ops.bh_adjust(pout, "pairwise", out=padj)
+                bev[i + 1].record()
+            barrier()
+            b_ms = max_over_ranks(float(np.median([bev[i].elapsed_time(bev[i + 1]) for i in range(3)])))
+            fisher["bh"] = {"ms_per_step": b_ms, "value": tests_total / (b_ms * 1e-3), "unit": "p-values/s",
+                            "what": "sd_bh_adjust, one Benjamini-Hochberg adjustment per sample pair (column) "
+                                    "of the p-value matrix (pairwise_fisher.py:186-191)"}
+            del padj
+        except torch.OutOfMemoryError:
+            fisher["bh"] = None
         # host-buffer API for the e2e figure (p-values come back to the host)
         if not args.no_e2e:
-            inc_h_all = inc.cpu().numpy(); exc_h_all = exc.cpu().numpy()
+            inc_h_all = torch.empty(inc.shape, dtype=torch.int32).pin_memory(); inc_h_all.copy_(inc)
+            exc_h_all = torch.empty(exc.shape, dtype=torch.int64).pin_memory(); exc_h_all.copy_(exc)
             out_h = torch.empty((Jfr, len(pa)), dtype=torch.float64).pin_memory()
             ops.fisher_pairwise_host(inc_h_all, exc_h_all, pa, pb, out=out_h, device=local_rank)
             barrier()
@@ -491,7 +515,7 @@ def main():
             barrier()
             dt = max_over_ranks(time.perf_counter() - t0)
             fisher["e2e"] = {"value": tests_total / dt, "unit": "tests/s", "ms_per_step": dt * 1e3,
-                             "h2d_bytes_per_step": int(inc_h_all.nbytes + exc_h_all.nbytes),
+                             "h2d_bytes_per_step": int(inc_h_all.numel() * 4 + exc_h_all.numel() * 8),
                              "d2h_bytes_per_step": int(out_h.numel() * 8)}
             del out_h
         del pout

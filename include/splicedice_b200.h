@@ -177,7 +177,7 @@ int sd_fisher_tables(int64_t n_tables, const int64_t *a, const int64_t *b,
  * in IEEE binary64, so results are bit-identical to the numpy expression statsmodels evaluates.
  * p / out: DEVICE matrices [n_rows, n_cols] (out may alias p); at most 2^31 - 1 values per call
  * (SD_ERR_UNSUPPORTED beyond: column blocks are independent, split them).  Asynchronous on
- * `stream`; scratch comes from a caller-provided device workspace (~25 bytes per value).
+ * `stream`; scratch comes from a caller-provided device workspace (~33 bytes per value).
  */
 #define SD_BH_COLUMNS 0
 #define SD_BH_ALL 1

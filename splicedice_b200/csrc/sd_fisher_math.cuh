@@ -163,16 +163,74 @@ SD_HD double tail_fast(double p, double q, double u, double v)
     return t.A / t.Q;
 }
 
-// f(x) = log(pmf(x) / pmf(a)) in double-double.  Out of line, with everything passed by value,
-// so the (rare) call does not force the caller's state into local memory.
+// exp(x) for x <= ~1 (log-probabilities): k = rint(x / ln 2), r = x - k ln 2 in two FMA steps,
+// degree-13 Taylor polynomial on |r| <= 0.347 (truncation 4e-18), scaling by 2^k on the exponent
+// field.  ~2 ulp; x < -746 gives 0, results below 2^-1022 are rounded once by a final multiply.
+// The coefficients sit in constant memory so every DFMA takes its constant operand directly
+// (libdevice's exp spends two UMOV per coefficient on this target).
+#ifdef __CUDA_ARCH__
+#define SD_EXP_COEF __constant__
+#else
+#define SD_EXP_COEF static const
+#endif
+SD_EXP_COEF double kExpCoef[12] = {
+    1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0,
+    1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5};
+
+SD_HD double add_exponent(double x, int k)      // x * 2^k, result normal
+{
+#ifdef __CUDA_ARCH__
+    return __hiloint2double(__double2hiint(x) + (k << 20), __double2loint(x));
+#else
+    return ldexp(x, k);
+#endif
+}
+
+SD_HD double exp_small(double x)
+{
+    if (!(x >= -746.0)) return 0.0;
+    const double kMagic = 6755399441055744.0;                  // 2^52 + 2^51: rint() in the low fraction bits
+    const double t = fma(x, 1.4426950408889634, kMagic);
+    const double kf = t - kMagic;
+    double r = fma(kf, -6.9314718055994529e-01, x);
+    r = fma(kf, -2.3190468138462996e-17, r);
+    double q = kExpCoef[0];
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int i = 1; i < 12; ++i) q = fma(q, r, kExpCoef[i]);
+    q = fma(q, r, 1.0);
+    q = fma(q, r, 1.0);
+    const int k = (int)kf;
+    if (k >= -1020) return add_exponent(q, k);
+    return add_exponent(q, k + 1000) * 9.3326361850321888e-302;   // 2^-1000
+}
+
+// (hi, lo) of a compensated sum: renormalise the TwoSum accumulator pair
+SD_HD dd acc_result(double sum, double err)
+{
+    const double hi = sum + err;
+    return dd_make(hi, err - (hi - sum));
+}
+
+// f(x) = log(pmf(x) / pmf(a)) in double-double: G(a) - G(x) as one compensated sum of the eight
+// table entries (TwoSum on the hi words, rounding errors and lo words accumulated separately --
+// the error words are ~1e-12, so their plain-double sum is good to ~1e-27).  Out of line, with
+// everything passed by value, so the call does not force the caller's state into local memory.
 template <class Table, class Int>
 SD_NOINLINE dd f_exact_of(Table tab, Int a, Int b, Int c, Int d, Int n1, Int n2, Int n, Int x)
 {
-    dd s = dd_sub(tab.get(a), tab.get(x));
-    s = dd_add(s, dd_sub(tab.get(b), tab.get(n1 - x)));
-    s = dd_add(s, dd_sub(tab.get(c), tab.get(n - x)));
-    s = dd_add(s, dd_sub(tab.get(d), tab.get(n2 - n + x)));
-    return s;
+    const dd t0 = tab.get(a), t1 = tab.get(x), t2 = tab.get(b), t3 = tab.get(n1 - x);
+    const dd t4 = tab.get(c), t5 = tab.get(n - x), t6 = tab.get(d), t7 = tab.get(n2 - n + x);
+    double sum = t0.hi, err = t0.lo;
+    acc_two_sum(sum, err, -t1.hi, -t1.lo);
+    acc_two_sum(sum, err, t2.hi, t2.lo);
+    acc_two_sum(sum, err, -t3.hi, -t3.lo);
+    acc_two_sum(sum, err, t4.hi, t4.lo);
+    acc_two_sum(sum, err, -t5.hi, -t5.lo);
+    acc_two_sum(sum, err, t6.hi, t6.lo);
+    acc_two_sum(sum, err, -t7.hi, -t7.lo);
+    return acc_result(sum, err);
 }
 
 // G(x) = lg[x] + lg[n1-x] + lg[n-x] + lg[n2-n+x]; log pmf(x) = const - G(x).
@@ -302,11 +360,11 @@ SD_HD Plan<Int> make_plan(const Table &tab, Int a, Int b, Int c, Int d)
     pl.near[0] = a; pl.near[1] = d; pl.near[2] = b; pl.near[3] = c;                  // a, a-1, ...
     if (g <= hi) {
         const dd fg = pr.f_exact(g);
-        double tg = exp(fg.hi);
+        double tg = exp_small(fg.hi);
         pl.tg = fma(tg, fg.lo, tg);
         pl.far[0] = n1 - g; pl.far[1] = n - g; pl.far[2] = g; pl.far[3] = n2 - n + g;
     }
-    double pexact = exp(lp_hi);
+    double pexact = exp_small(lp_hi);
     pl.pexact = fma(pexact, lp_lo, pexact);
     return pl;
 }

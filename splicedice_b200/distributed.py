@@ -15,6 +15,38 @@ import torch.distributed as dist
 from . import sharding
 
 
+def bind_to_gpu_numa(device: int = 0):
+    """Pin the calling thread (and the threads it starts later) to the CPUs NVML reports as local
+    to ``device``, so pinned host buffers allocated afterwards land on the GPU's own NUMA node and
+    its PCIe traffic does not cross the socket interconnect.  One process per GPU calls this once,
+    before it allocates host buffers.  Performance only: returns the CPU set used, or None when
+    NVML / the affinity call is unavailable or the local CPUs are outside this process's cpuset."""
+    import os
+    if os.environ.get("SD_NO_NUMA_BIND"):
+        return None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        index = device
+        if visible:
+            ids = [v.strip() for v in visible.split(",") if v.strip()]
+            if device < len(ids) and ids[device].isdigit():
+                index = int(ids[device])
+        handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (n_cpu + 63) // 64)
+        local = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus = local & allowed
+        if not cpus or cpus == allowed:
+            return None if not cpus else sorted(cpus)
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:                          # noqa: BLE001 - placement hint only
+        return None
+
+
 def _world():
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(), dist.get_world_size()
@@ -65,3 +97,103 @@ def quant_ps_sharded(counts_host, row_ptr, col_idx, device=None, gather=True, lo
     if low_mask is not None:
         raise NotImplementedError("low_mask is applied per slab by the caller")
     return sharded_rows(counts_host, row_ptr, col_idx, slab, gather=gather)
+
+
+# ---- pairwise: row-sharded Fisher, column-sharded Benjamini-Hochberg ---------------------------
+# The Fisher rows are independent, so every rank computes p[rows_r, P] for its row slab.  The
+# per-pair correction (pairwise_fisher.py:186-191) ranks each COLUMN over all junctions, which is
+# the path's one real exchange step: an all-to-all turns the row slabs into column blocks
+# [J, P_r] (NCCL over NVLink on CUDA tensors), each rank adjusts its columns with sd_bh_adjust,
+# and a second all-to-all brings the adjusted values back to the row owners.
+
+def _all_to_all(recv, send):
+    """recv[g] <- rank g's send[this rank].  One NCCL all-to-all on CUDA tensors; backends without
+    that collective (gloo, in the CPU tests) exchange the same blocks with paired isend / irecv."""
+    rank, world = _world()
+    if dist.get_backend() == "nccl":
+        dist.all_to_all(recv, send)
+        return
+    recv[rank].copy_(send[rank])
+    ops_ = []
+    for g in range(world):
+        if g != rank:
+            ops_.append(dist.P2POp(dist.isend, send[g], g))
+            ops_.append(dist.P2POp(dist.irecv, recv[g], g))
+    for req in dist.batch_isend_irecv(ops_):
+        req.wait()
+
+
+def column_blocks(n_cols, world):
+    """Contiguous, near-equal column ranges, one per rank."""
+    base, extra = divmod(n_cols, world)
+    cuts = [0]
+    for g in range(world):
+        cuts.append(cuts[-1] + base + (1 if g < extra else 0))
+    return [(cuts[g], cuts[g + 1]) for g in range(world)]
+
+
+def rows_to_columns(p_local, parts):
+    """[rows_r, P] on every rank -> [J, P_r] on every rank (rows in global order)."""
+    rank, world = _world()
+    blocks = column_blocks(p_local.shape[1], world)
+    if world == 1:
+        return p_local
+    send = [p_local[:, a:b].contiguous() for a, b in blocks]
+    c0, c1 = blocks[rank]
+    recv = [torch.empty((r1 - r0, c1 - c0), dtype=p_local.dtype, device=p_local.device) for r0, r1 in parts]
+    _all_to_all(recv, send)
+    return torch.cat(recv, dim=0)
+
+
+def columns_to_rows(q_cols, parts, n_cols):
+    """Inverse of rows_to_columns: [J, P_r] -> [rows_r, P]."""
+    rank, world = _world()
+    if world == 1:
+        return q_cols
+    blocks = column_blocks(n_cols, world)
+    r0, r1 = parts[rank]
+    send = [q_cols[a:b].contiguous() for a, b in parts]
+    recv = [torch.empty((r1 - r0, b - a), dtype=q_cols.dtype, device=q_cols.device) for a, b in blocks]
+    _all_to_all(recv, send)
+    return torch.cat(recv, dim=1)
+
+
+def bh_columns_sharded(p_local, parts, adjust_fn):
+    """Per-column Benjamini-Hochberg of a row-sharded p-value matrix.  ``adjust_fn([J, P_r]) ->
+    [J, P_r]`` adjusts whole columns (ops.bh_adjust(..., 'pairwise') in the product; the numpy
+    restatement in the gloo test)."""
+    n_cols = p_local.shape[1]
+    cols = rows_to_columns(p_local, parts)
+    return columns_to_rows(adjust_fn(cols), parts, n_cols)
+
+
+def pairwise_sharded(counts_host, row_ptr, col_idx, correction="pairwise", device=None):
+    """``splicedice pairwise`` arithmetic over the ranks' GPUs: exclusion sums + Fisher on this
+    rank's row slab, then the correction.  counts_host: integer [J, S] on every rank (each uploads
+    only its slab).  Returns (float64 CUDA tensor [rows_r, P], (r0, r1))."""
+    from . import ops
+    rank, world = _world()
+    if correction not in ("none", "pairwise", "all"):
+        raise ValueError("correction must be 'none', 'pairwise' or 'all'")
+    if correction == "all" and world > 1:
+        raise NotImplementedError("'all' ranks every p-value of the matrix together: run it on one GPU")
+    dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+    parts = sharding.partition_rows(row_ptr, col_idx, world)
+    r0, r1 = parts[rank]
+    rp, ci = sharding.shard_csr(row_ptr, col_idx, r0, r1)
+    slab = np.ascontiguousarray(counts_host[r0:r1]).astype(np.int64)
+    if (slab < 0).any():
+        raise ValueError("All values in `table` must be nonnegative.")
+    S = slab.shape[1]
+    buf = torch.zeros((r1 - r0, (S + 3) // 4 * 4), dtype=torch.int32, device=dev)
+    buf[:, :S] = torch.from_numpy(slab.astype(np.int32)).to(dev)
+    inc = buf[:, :S]
+    exc = ops.quant_ps(inc, rp, ci, want_f32=False, want_exc=True)["exc"]
+    pa, pb = ops.all_pairs(S)
+    bound = int(slab.max(initial=0)) * (1 + int(np.diff(rp).max(initial=0)))
+    p = ops.fisher_pairwise(inc, exc, pa, pb, max_cell_bound=bound)
+    if correction == "pairwise":
+        p = bh_columns_sharded(p, parts, lambda cols: ops.bh_adjust(cols, "pairwise", out=cols))
+    elif correction == "all":
+        ops.bh_adjust(p, "all", out=p)
+    return p, (r0, r1)

@@ -93,3 +93,51 @@ def test_two_rank_gather_over_gloo(tmp_path):
                        capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
+
+
+def test_two_rank_bh_exchange_over_gloo(tmp_path):
+    """The pairwise correction's exchange step on CPU tensors (gloo, world_size 2): row slabs ->
+    column blocks -> per-column Benjamini-Hochberg (the numpy restatement stands in for
+    sd_bh_adjust) -> back to row slabs; equals the correction of the whole matrix."""
+    script = tmp_path / "worker_bh.py"
+    script.write_text(
+        "import os, sys\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "import numpy as np, torch, torch.distributed as dist\n"
+        "from oracle import oracle_np\n"
+        "from splicedice_b200 import distributed\n"
+        "dist.init_process_group('gloo')\n"
+        "rank, world = dist.get_rank(), dist.get_world_size()\n"
+        "rng = np.random.default_rng(5)\n"
+        "p = rng.random((1001, 7)) ** 3\n"
+        "p[rng.random(p.shape) < 0.1] = 1.0\n"
+        "parts = [(0, 430), (430, 1001)]\n"
+        "def adjust(cols):\n"
+        "    out = cols.numpy().copy()\n"
+        "    for k in range(out.shape[1]):\n"
+        "        out[:, k] = oracle_np.bh_adjust(out[:, k])\n"
+        "    return torch.from_numpy(out)\n"
+        "r0, r1 = parts[rank]\n"
+        "cols = distributed.rows_to_columns(torch.from_numpy(p[r0:r1].copy()), parts)\n"
+        "c0, c1 = distributed.column_blocks(7, world)[rank]\n"
+        "assert np.array_equal(cols.numpy(), p[:, c0:c1])\n"
+        "got = distributed.bh_columns_sharded(torch.from_numpy(p[r0:r1].copy()), parts, adjust)\n"
+        "want = np.stack([oracle_np.bh_adjust(p[:, k]) for k in range(7)], axis=1)[r0:r1]\n"
+        "assert np.array_equal(got.numpy().view(np.uint64), want.view(np.uint64))\n"
+        "dist.destroy_process_group()\n"
+        "print('rank', rank, 'ok')\n")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("ok") == 2
+
+
+def test_column_blocks_cover_all_columns():
+    from splicedice_b200 import distributed
+    for n, w in [(7, 2), (2016, 8), (3, 8), (0, 2)]:
+        blocks = distributed.column_blocks(n, w)
+        assert len(blocks) == w and blocks[0][0] == 0 and blocks[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
+        assert max(b - a for a, b in blocks) - min(b - a for a, b in blocks) <= 1
