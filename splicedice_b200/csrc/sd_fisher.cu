@@ -4,12 +4,15 @@
 // (/root/reference/splicedice/pairwise_fisher.py:154-180) and scipy.stats.fisher_exact's
 // two-sided branch; the per-table arithmetic is in sd_fisher_math.cuh.
 //
-// Mapping: one warp per (junction, 32-pair tile), one table per lane; persistent CTAs stride
-// over the tiles.  The double-double log-factorial table is staged once per CTA in shared
-// memory (entries beyond the staged prefix come from the global copy through L1/L2).  The
-// junction's inclusion / exclusion row is a few hundred bytes and is gathered through L1; the
-// 32 p-values of a tile leave as one 256-byte coalesced store.  The kernel is FP64-pipe bound:
-// ~9 FP64 instructions per summed tail term, no division or exp in the loop.
+// Mapping: one table per lane.  Default (every table total below 2^30): the cost-binned kernel --
+// one persistent 1,024-thread CTA per SM made of four independent 256-thread groups that share a
+// single shared-memory copy of the double-double log-factorial table; a group takes up to 2,048
+// pairs of one junction, stages the junction's inclusion / exclusion row in shared memory,
+// counting-sorts the pairs by predicted tail length and hands out groups of 32 similar pairs to
+// its warps.  Fallback / 64-bit totals: one warp per (junction, 32-pair tile) in pair order.
+// Entries beyond the staged table prefix come from the global copy through L1/L2.  The kernel is
+// FP64-pipe / issue bound: 7 FP64 instructions per summed tail term, no division or exp in the
+// loop, cut and rescale tests on the exponent words with integer instructions.
 #include <algorithm>
 #include <mutex>
 #include <vector>

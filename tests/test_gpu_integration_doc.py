@@ -66,3 +66,9 @@ def test_documented_stubs_run_and_match():
     q = fisher_c.pairwise(ns["inc"].astype(np.int64), ns["exc"], pa, pb)
     ok = q > 1e-300
     assert (np.abs(ns["parray"][ok] - q[ok]) / q[ok]).max() < 1e-9
+
+    # multiple-test correction: the documented sd_bh_adjust call, per column
+    raw = ns["parray"].copy()
+    exec(blocks[4], ns)
+    want_adj = np.stack([oracle_np.bh_adjust(raw[:, k]) for k in range(raw.shape[1])], axis=1)
+    np.testing.assert_array_equal(ns["corrected"].view(np.uint64), want_adj.view(np.uint64))
