@@ -110,6 +110,7 @@ int sd_cluster_fill(int64_t n_junctions, int64_t nnz, const int32_t *row_of_pos,
 #define SD_QUANT_VEC1 0x20000u           /* wide kernel: 128-column slabs (4 columns per lane) */
 #define SD_QUANT_VEC2 0x40000u           /* wide kernel: 256-column slabs (8 columns per lane) */
 #define SD_QUANT_NARROW_TILES 0x10000u   /* force the narrow-matrix tile kernel for any n_samples (tests) */
+#define SD_QUANT_GENERAL 0x80000u        /* wide kernel: the general epilogue even for a single output (tests) */
 int sd_quant_ps(int64_t n_junctions, int32_t n_samples,
                 const int32_t *counts, int64_t ld_counts,
                 const int32_t *row_ptr, const int32_t *col_idx,

@@ -15,7 +15,7 @@ from . import build as _build
 SD_OK = 0
 SD_ERR_INVALID, SD_ERR_CUDA, SD_ERR_WORKSPACE, SD_ERR_OVERFLOW, SD_ERR_UNSUPPORTED = 1, 2, 3, 4, 5
 SD_QUANT_AUTO, SD_QUANT_GATHER, SD_QUANT_TILED = 0, 1, 2
-SD_QUANT_NARROW_TILES, SD_QUANT_VEC1, SD_QUANT_VEC2 = 0x10000, 0x20000, 0x40000
+SD_QUANT_NARROW_TILES, SD_QUANT_VEC1, SD_QUANT_VEC2, SD_QUANT_GENERAL = 0x10000, 0x20000, 0x40000, 0x80000
 ABI_VERSION = 1
 
 

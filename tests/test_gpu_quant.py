@@ -206,3 +206,38 @@ def test_sums_beyond_32_bits_take_the_wide_path():
         want64 = inc / (inc + exc)
     np.testing.assert_array_equal(util.bits64(got["ps_f64"]), util.bits64(want64))
     np.testing.assert_array_equal(util.bits32(got["ps_f32"]), util.bits32(want64.astype(np.float32)))
+
+
+def test_f64_divide_exhaustive_and_random():
+    """The float64 lean epilogue (div_fast: reciprocal + residual correction without the range
+    check) against numpy's float64 divide: every pair 0 <= a <= b <= 2048 and 4M random pairs
+    with b up to 2^32 - 2, through the lean and the general epilogue."""
+    native, ops = _ops()
+    b = np.repeat(np.arange(1, 2049), np.arange(2, 2050))
+    a = np.concatenate([np.arange(0, k + 1) for k in range(1, 2049)])
+    rng = np.random.default_rng(6)
+    hi = rng.integers(0, 2 ** 31, size=4_000_000)
+    lo = rng.integers(0, 2 ** 31, size=4_000_000)
+    small = rng.random(hi.size) < 0.5
+    hi[small] >>= rng.integers(0, 31, size=int(small.sum()))
+    lo[small] >>= rng.integers(0, 31, size=int(small.sum()))
+    edge = np.array([[2 ** 31 - 1, 2 ** 31 - 1], [0, 2 ** 31 - 1], [2 ** 31 - 1, 0], [1, 2 ** 31 - 1], [0, 0], [3, 0]])
+    inc = np.concatenate([a, hi, edge[:, 0]]); exc = np.concatenate([b - a, lo, edge[:, 1]])
+    S = 1024
+    pad = (-inc.size) % S
+    inc = np.concatenate([inc, np.zeros(pad, dtype=np.int64)]); exc = np.concatenate([exc, np.ones(pad, dtype=np.int64)])
+    M = inc.size // S
+    counts = np.empty((2 * M, S), dtype=np.int32)
+    counts[0::2] = inc.reshape(M, S)
+    counts[1::2] = exc.reshape(M, S)
+    row_ptr = np.arange(2 * M + 1, dtype=np.int32)
+    col_idx = (np.arange(2 * M, dtype=np.int32) ^ 1)
+    c = torch.from_numpy(counts).cuda()
+    tot = np.repeat((inc + exc).reshape(M, S), 2, axis=0).astype(np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        want = counts.astype(np.float64) / tot
+    lean = ops.quant_ps(c, row_ptr, col_idx, want_f32=False, want_f64=True)["ps_f64"].cpu().numpy()
+    np.testing.assert_array_equal(lean.view(np.uint64), want.view(np.uint64))
+    general = ops.quant_ps(c, row_ptr, col_idx, want_f32=False, want_f64=True,
+                           flags=native.SD_QUANT_GENERAL)["ps_f64"].cpu().numpy()
+    np.testing.assert_array_equal(general.view(np.uint64), want.view(np.uint64))

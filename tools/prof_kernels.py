@@ -109,8 +109,38 @@ def misc():
             print(f"quant f64 PS {J}x{S}: {ms:.3f} ms/launch, {J * S * 12 / ms / 1e6:.0f} GB/s algorithmic (12 B/cell)")
 
 
+def variants():
+    """configs[4] (ir_table ratio) and the float64 PS of counts_to_ps at 400,000 x 1,000: CUDA events."""
+    dev = torch.device("cuda", 0)
+    J = int(sys.argv[2]) if len(sys.argv) > 2 else 400_000
+    S = int(sys.argv[3]) if len(sys.argv) > 3 else 1000
+    cl = ops.cluster_build(*synth.junction_arrays(J, 3)[:4])
+    counts = ops.synth_counts(1, 0, J, S, device=dev)
+    med = torch.rand((J, S), dtype=torch.float64, device=dev).mul_(10).floor_()
+    ir = torch.empty((J, S), dtype=torch.float64, device=dev)
+    ps64 = torch.empty((J, S), dtype=torch.float64, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    from splicedice_b200 import native
+    for name, fn, bytes_per_cell in (
+            ("ir_ratio", lambda: native.call("sd_ir_ratio", J, S, native.ptr(med), med.stride(0), native.ptr(counts),
+                                             counts.stride(0), native.ptr(cl["row_ptr"]), native.ptr(cl["col_idx"]),
+                                             native.ptr(ir), ir.stride(0), 0, J, native.stream_ptr()), 20),
+            ("quant f64 PS", lambda: ops.quant_ps(counts, cl["row_ptr"], cl["col_idx"], want_f32=False, out_f64=ps64), 12)):
+        for i in range(7):
+            if i == 2:
+                e0.record()
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        print(f"{name} {J}x{S}: {ms:.3f} ms/launch, {J * S * bytes_per_cell / ms / 1e6:.0f} GB/s algorithmic ({bytes_per_cell} B/cell)")
+
+
 if len(sys.argv) > 1 and sys.argv[1] == "misc":
     misc()
+    sys.exit(0)
+if len(sys.argv) > 1 and sys.argv[1] == "variants":
+    variants()
     sys.exit(0)
 
 
