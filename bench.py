@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--fisher-junctions", type=int, default=200_000)
     ap.add_argument("--fisher-samples", type=int, default=64)
     ap.add_argument("--no-fisher", action="store_true")
+    ap.add_argument("--no-variants", action="store_true", help="skip the float64 PS / intron-retention timings")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-rows", type=int, default=150_000, help="rows of the CPU-baseline sample")
@@ -427,6 +428,43 @@ def main():
                "host_cpus_local_to_gpu": len(numa_cpus) if numa_cpus else None}
         del h_counts, h_ps
 
+    # ---- the other epilogues of the same kernel on the same slab: counts_to_ps's float64 PS and
+    # ir_table's intron-retention ratio (BASELINE.json configs[4]) --------------------------------
+    variants = None
+    if not args.no_variants:
+        variants = {}
+        try:
+            med = torch.rand((Jr, S), dtype=torch.float64, device=dev).mul_(10).floor_()
+            out64 = torch.empty((Jr, S), dtype=torch.float64, device=dev)
+
+            def run_ir():
+                native.call("sd_ir_ratio", Jr, S, native.ptr(med), med.stride(0), native.ptr(counts), counts.stride(0),
+                            native.ptr(d_rp), native.ptr(d_ci), native.ptr(out64), out64.stride(0), 0, Jr,
+                            native.stream_ptr())
+
+            def run_f64():
+                ops.quant_ps(counts, d_rp, d_ci, want_f32=False, out_f64=out64)
+
+            for key, fn, bpc, what in (
+                    ("ir_ratio", run_ir, 20, "sd_ir_ratio: median f64 + counts i32 -> IR f64 (ir_table.py:118-132; configs[4])"),
+                    ("ps_f64", run_f64, 12, "sd_quant_ps float64 PS (counts_to_ps.py:62-68)")):
+                for _ in range(2):
+                    fn()
+                barrier()
+                v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                v0.record()
+                for _ in range(5):
+                    fn()
+                v1.record()
+                barrier()
+                v_ms = max_over_ranks(v0.elapsed_time(v1) / 5)
+                gbs = cells_rank * bpc / (v_ms * 1e-3) / 1e9
+                variants[key] = {"ms_per_step": v_ms, "value": cells_total / (v_ms * 1e-3), "unit": UNIT,
+                                 "bytes_per_cell": bpc, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peak, "what": what}
+            del med, out64
+        except torch.OutOfMemoryError:
+            variants = None
+
     # ---- pairwise Fisher (configs[2]) ----------------------------------------------------------
     fisher = None
     if not args.no_fisher:
@@ -553,7 +591,7 @@ def main():
                          "traffic": traffic, "traffic_source": traffic_src, "kernel": "quant_wide_kernel<2, true>", "kernel_ms": kernel_ms,
                          "bytes_per_cell": 8, "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps, "launch_mode": "cuda graph of K kernel launches" if graph is not None else "K stream launches",
-            "clocks": clocks, "fisher": fisher,
+            "clocks": clocks, "variants": variants, "fisher": fisher,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

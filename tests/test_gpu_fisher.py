@@ -126,3 +126,39 @@ def test_bounded_entry_point_matches_and_guards():
     bad = over[:, pa] | over[:, pb]
     assert bad.any() and np.isnan(tight[bad]).all()
     np.testing.assert_array_equal(tight[~bad], ref[~bad])
+
+
+def test_kernel_instantiations_agree():
+    """Every instantiation of the pairwise kernel on the same tables: staged table (mode 0), table
+    partly / wholly in global memory (modes 1, 2 with the lgamma fallback, chosen through the
+    promised bound), 64-bit totals (the pair-order kernel), the plain kernel by environment
+    switch -- and more than 512 samples, where the junction row is not staged in shared memory."""
+    import os
+    _, ops = _ops()
+    J, S = 700, 10
+    _, csr, counts = util.synthetic_problem(J, S, seed=33, zero_frac=0.1)
+    exc = oracle_np.exclusion_sums(counts, csr["row_ptr"], csr["col_idx"])
+    pa, pb = oracle_np.all_pairs(S)
+    dev = torch.device("cuda", 0)
+    inc_d, exc_d = torch.from_numpy(counts).to(dev), torch.from_numpy(exc).to(dev)
+    want = fisher_c.pairwise(counts, exc, pa, pb)
+    for bound in (int((counts + exc).max()), 20_000, 3_000_000, 2 ** 31):
+        got = ops.fisher_pairwise(inc_d, exc_d, pa, pb, max_cell_bound=bound).cpu().numpy()
+        _check(got.ravel(), want.ravel(), rtol=1e-11)
+    os.environ["SD_FISHER_PLAIN"] = "1"
+    try:
+        got = ops.fisher_pairwise(inc_d, exc_d, pa, pb).cpu().numpy()
+    finally:
+        del os.environ["SD_FISHER_PLAIN"]
+    _check(got.ravel(), want.ravel(), rtol=1e-11)
+
+    # 600 samples (> 512: unstaged row), an arbitrary pair list with repeats and a == b
+    J2, S2 = 40, 600
+    _, csr2, counts2 = util.synthetic_problem(J2, S2, seed=34, zero_frac=0.05)
+    exc2 = oracle_np.exclusion_sums(counts2, csr2["row_ptr"], csr2["col_idx"])
+    rng = np.random.default_rng(0)
+    qa = rng.integers(0, S2, size=3001).astype(np.int32)
+    qb = rng.integers(0, S2, size=3001).astype(np.int32)
+    got2 = ops.fisher_pairwise(torch.from_numpy(counts2).to(dev), torch.from_numpy(exc2).to(dev), qa, qb).cpu().numpy()
+    want2 = fisher_c.pairwise(counts2, exc2, qa, qb)
+    _check(got2.ravel(), want2.ravel(), rtol=1e-11)
