@@ -241,3 +241,46 @@ def test_f64_divide_exhaustive_and_random():
     general = ops.quant_ps(c, row_ptr, col_idx, want_f32=False, want_f64=True,
                            flags=native.SD_QUANT_GENERAL)["ps_f64"].cpu().numpy()
     np.testing.assert_array_equal(general.view(np.uint64), want.view(np.uint64))
+
+
+@pytest.mark.parametrize("shape", [(5000, 200), (1200, 1000), (700, 1001), (33, 193), (2100, 512), (100, 260),
+                                   (47, 1000), (49, 300), (1, 257)])
+def test_lean_single_output_forms(shape):
+    """One output at a time (the lean binary32 / binary64 epilogues) against the oracle bit for bit."""
+    native, ops = _ops()
+    J, S = shape
+    _, csr, counts = util.synthetic_problem(J, S, seed=3 * J + S, zero_frac=0.3)
+    dev = torch.device("cuda", 0)
+    buf = torch.zeros((J, (S + 3) // 4 * 4), dtype=torch.int32, device=dev)
+    buf[:, :S] = torch.from_numpy(counts).to(dev)
+    view = buf[:, :S]
+    flags = native.SD_QUANT_TILED
+    out32 = torch.full((J, (S + 3) // 4 * 4), 7.0, dtype=torch.float32, device=dev)
+    out64 = torch.full((J, (S + 3) // 4 * 4), 7.0, dtype=torch.float64, device=dev)
+    ops.quant_ps(view, csr["row_ptr"], csr["col_idx"], out_f32=out32[:, :S], flags=flags)
+    ops.quant_ps(view, csr["row_ptr"], csr["col_idx"], want_f32=False, out_f64=out64[:, :S], flags=flags)
+    exc = oracle_np.exclusion_sums(counts, csr["row_ptr"], csr["col_idx"])
+    want32 = oracle_np.ps_f32(counts, csr["row_ptr"], csr["col_idx"], exc=exc)
+    want64 = oracle_np.ps_f64(counts, csr["row_ptr"], csr["col_idx"], exc=exc)
+    np.testing.assert_array_equal(util.bits32(out32[:, :S].cpu().numpy()), util.bits32(want32))
+    np.testing.assert_array_equal(util.bits64(out64[:, :S].cpu().numpy()), util.bits64(want64))
+    assert (out32[:, S:] == 7.0).all() and (out64[:, S:] == 7.0).all()          # padding untouched
+
+
+def test_lean_forms_on_adversarial_adjacency():
+    """Deep nests (degree >= 100: adjacency lists beyond the staged capacity), touching
+    intervals and singletons from the reference-made adversarial fixture, wide random counts."""
+    native, ops = _ops()
+    g = util.load_npz("quant_adversarial.npz")
+    csr = dict(row_ptr=g["row_ptr"].astype(np.int32), col_idx=g["col_idx"].astype(np.int32))
+    J = len(csr["row_ptr"]) - 1
+    S = 300
+    counts = np.random.default_rng(12).integers(0, 60, size=(J, S)).astype(np.int32)
+    counts[np.random.default_rng(13).random((J, S)) < 0.4] = 0
+    c = torch.from_numpy(counts).cuda()
+    flags = native.SD_QUANT_TILED
+    got32 = ops.quant_ps(c, csr["row_ptr"], csr["col_idx"], flags=flags)["ps_f32"].cpu().numpy()
+    got64 = ops.quant_ps(c, csr["row_ptr"], csr["col_idx"], want_f32=False, want_f64=True, flags=flags)["ps_f64"].cpu().numpy()
+    exc = oracle_np.exclusion_sums(counts, csr["row_ptr"], csr["col_idx"])
+    np.testing.assert_array_equal(util.bits32(got32), util.bits32(oracle_np.ps_f32(counts, csr["row_ptr"], csr["col_idx"], exc=exc)))
+    np.testing.assert_array_equal(util.bits64(got64), util.bits64(oracle_np.ps_f64(counts, csr["row_ptr"], csr["col_idx"], exc=exc)))
