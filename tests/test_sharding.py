@@ -141,3 +141,17 @@ def test_column_blocks_cover_all_columns():
         assert len(blocks) == w and blocks[0][0] == 0 and blocks[-1][1] == n
         assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
         assert max(b - a for a, b in blocks) - min(b - a for a, b in blocks) <= 1
+
+
+def test_numa_binding_is_a_harmless_hint():
+    """bind_to_gpu_numa never raises: without NVML / a GPU it returns None and leaves the affinity alone."""
+    from splicedice_b200 import distributed
+    before = os.sched_getaffinity(0)
+    got = distributed.bind_to_gpu_numa(0)
+    assert got is None or set(got) <= before
+    os.sched_setaffinity(0, before)
+    os.environ["SD_NO_NUMA_BIND"] = "1"
+    try:
+        assert distributed.bind_to_gpu_numa(0) is None
+    finally:
+        del os.environ["SD_NO_NUMA_BIND"]
