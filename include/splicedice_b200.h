@@ -216,6 +216,14 @@ int sd_rsd5(int64_t n, const double *cov5, double *rsd_out, void *stream);
 int sd_host_format_rows(int kind, const void *matrix, int64_t rows, int32_t cols, int64_t ld,
                         const char *names, const int64_t *name_off, char *out, size_t cap,
                         size_t *written, int n_threads);
+/* Same formatting, without the final compaction: every thread leaves its rows' text in its own
+ * slice of `out`; segment k is out[seg_off[k], seg_off[k] + seg_len[k]) for k < *n_segments
+ * (<= max_segments), to be written in order.  SD_ERR_WORKSPACE with *needed set if cap is too
+ * small.  The file writers stream ~64 MB row chunks through one reusable buffer this way. */
+int sd_host_format_rows_segments(int kind, const void *matrix, int64_t rows, int32_t cols, int64_t ld,
+                                 const char *names, const int64_t *name_off, char *out, size_t cap,
+                                 int64_t *seg_off, int64_t *seg_len, int32_t max_segments,
+                                 int32_t *n_segments, size_t *needed, int n_threads);
 
 /* Table reader for "header\nname<TAB>v<TAB>...\n" files (the reference parses them one python
  * float per cell: counts_to_ps.py:43-51, pairwise_fisher.py:46-61, ir_table.py:72-80).

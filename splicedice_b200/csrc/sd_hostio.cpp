@@ -25,16 +25,46 @@
 
 namespace {
 
-inline void put_uint(std::string &s, uint64_t v)
+// Bounded output cursor over caller memory.  Writes past `end` are dropped and counted, so a
+// too-small buffer yields the exact size needed instead of an overrun.
+struct Sink {
+    char *p, *end;
+    size_t dropped = 0;
+    Sink(char *begin, char *end_) : p(begin), end(end_) {}
+    void push_back(char c)
+    {
+        if (p < end) *p++ = c;
+        else ++dropped;
+    }
+    void append(const char *q, size_t n)
+    {
+        if ((size_t)(end - p) >= n) { memcpy(p, q, n); p += n; }
+        else dropped += n;
+    }
+    void fill(size_t n, char c)
+    {
+        if ((size_t)(end - p) >= n) { memset(p, c, n); p += n; }
+        else dropped += n;
+    }
+};
+
+inline int uint_digits(char *buf, uint64_t v)      // decimal digits of v, most significant first
+{
+    char tmp[24];
+    int n = 0;
+    do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+    for (int i = 0; i < n; ++i) buf[i] = tmp[n - 1 - i];
+    return n;
+}
+
+inline void put_uint(Sink &s, uint64_t v)
 {
     char buf[24];
-    int n = 0;
-    do { buf[n++] = (char)('0' + v % 10); v /= 10; } while (v);
-    while (n) s.push_back(buf[--n]);
+    s.append(buf, (size_t)uint_digits(buf, v));
 }
 
 // %.3f of a finite double whose scaled value fits the exact path
-inline bool put_fixed3(std::string &s, double v)
+inline bool put_fixed3(Sink &s, double v)
 {
     const double av = fabs(v);
     if (!(av < 4.0e12)) return false;
@@ -47,20 +77,23 @@ inline bool put_fixed3(std::string &s, double v)
     if (t == 0.5 && e > 0.0) r += 1.0;
     else if (t == -0.5 && e < 0.0) r -= 1.0;
     const uint64_t q = (uint64_t)r;
-    if (signbit(v)) s.push_back('-');
-    put_uint(s, q / 1000);
+    char buf[32];
+    int n = 0;
+    if (signbit(v)) buf[n++] = '-';
+    n += uint_digits(buf + n, q / 1000);
     const unsigned f = (unsigned)(q % 1000);
-    s.push_back('.');
-    s.push_back((char)('0' + f / 100));
-    s.push_back((char)('0' + f / 10 % 10));
-    s.push_back((char)('0' + f % 10));
+    buf[n++] = '.';
+    buf[n++] = (char)('0' + f / 100);
+    buf[n++] = (char)('0' + f / 10 % 10);
+    buf[n++] = (char)('0' + f % 10);
+    s.append(buf, (size_t)n);
     return true;
 }
 
-inline void put_value_f(std::string &s, double v)
+inline void put_value_f(Sink &s, double v)
 {
-    if (isnan(v)) { s += "nan"; return; }
-    if (isinf(v)) { s += v < 0 ? "-inf" : "inf"; return; }
+    if (isnan(v)) { s.append("nan", 3); return; }
+    if (isinf(v)) { if (v < 0) s.append("-inf", 4); else s.append("inf", 3); return; }
     if (put_fixed3(s, v)) return;
     char buf[400];
     int n = snprintf(buf, sizeof buf, "%.3f", v);
@@ -69,56 +102,62 @@ inline void put_value_f(std::string &s, double v)
 
 // python's repr(float) / str(numpy.float64): shortest digits that round-trip, fixed notation when
 // the decimal exponent is in [-4, 16), otherwise d.ddde[+-]XX with at least two exponent digits
-inline void put_repr(std::string &s, double v)
+inline void put_repr(Sink &s, double v)
 {
-    if (isnan(v)) { s += "nan"; return; }
-    if (isinf(v)) { s += v < 0 ? "-inf" : "inf"; return; }
-    if (v == 0.0) { s += signbit(v) ? "-0.0" : "0.0"; return; }
+    if (isnan(v)) { s.append("nan", 3); return; }
+    if (isinf(v)) { if (v < 0) s.append("-inf", 4); else s.append("inf", 3); return; }
+    if (v == 0.0) { if (signbit(v)) s.append("-0.0", 4); else s.append("0.0", 3); return; }
     char buf[64];
     auto res = std::to_chars(buf, buf + sizeof buf, v, std::chars_format::scientific);   // d[.ddd]e[+-]XX, shortest
-    *res.ptr = 0;
     const char *p = buf, *end = res.ptr;
-    if (*p == '-') { s.push_back('-'); ++p; }
-    const char *e = p;
-    while (e < end && *e != 'e') ++e;
+    char out[64];
+    int n = 0;
+    if (*p == '-') { out[n++] = '-'; ++p; }
     char digits[40];
     int nd = 0;
-    for (const char *q = p; q < e; ++q)
-        if (*q != '.') digits[nd++] = *q;
-    const int exp10 = atoi(e + 1);
+    const char *e = p;
+    for (; e < end && *e != 'e'; ++e)
+        if (*e != '.') digits[nd++] = *e;
+    int exp10 = 0;
+    {
+        const char *q = e + 1;
+        const bool neg = *q == '-';
+        if (*q == '-' || *q == '+') ++q;
+        for (; q < end; ++q) exp10 = exp10 * 10 + (*q - '0');
+        if (neg) exp10 = -exp10;
+    }
     if (exp10 >= -4 && exp10 < 16) {
         if (exp10 < 0) {
-            s += "0.";
-            s.append((size_t)(-exp10 - 1), '0');
-            s.append(digits, (size_t)nd);
+            out[n++] = '0'; out[n++] = '.';
+            for (int i = 0; i < -exp10 - 1; ++i) out[n++] = '0';
+            memcpy(out + n, digits, (size_t)nd); n += nd;
         } else {
             const int int_digits = exp10 + 1;
             if (nd <= int_digits) {
-                s.append(digits, (size_t)nd);
-                s.append((size_t)(int_digits - nd), '0');
-                s += ".0";
+                memcpy(out + n, digits, (size_t)nd); n += nd;
+                for (int i = 0; i < int_digits - nd; ++i) out[n++] = '0';
+                out[n++] = '.'; out[n++] = '0';
             } else {
-                s.append(digits, (size_t)int_digits);
-                s.push_back('.');
-                s.append(digits + int_digits, (size_t)(nd - int_digits));
+                memcpy(out + n, digits, (size_t)int_digits); n += int_digits;
+                out[n++] = '.';
+                memcpy(out + n, digits + int_digits, (size_t)(nd - int_digits)); n += nd - int_digits;
             }
         }
     } else {
-        s.push_back(digits[0]);
-        if (nd > 1) { s.push_back('.'); s.append(digits + 1, (size_t)(nd - 1)); }
-        s.push_back('e');
-        s.push_back(exp10 < 0 ? '-' : '+');
+        out[n++] = digits[0];
+        if (nd > 1) { out[n++] = '.'; memcpy(out + n, digits + 1, (size_t)(nd - 1)); n += nd - 1; }
+        out[n++] = 'e';
+        out[n++] = exp10 < 0 ? '-' : '+';
         const int ae = exp10 < 0 ? -exp10 : exp10;
-        if (ae < 10) s.push_back('0');
-        put_uint(s, (uint64_t)ae);
+        if (ae < 10) out[n++] = '0';
+        n += uint_digits(out + n, (uint64_t)ae);
     }
+    s.append(out, (size_t)n);
 }
 
 template <class Get>
-void format_range(int64_t r0, int64_t r1, int32_t cols, const char *names, const int64_t *name_off, Get get,
-                  std::string *out)
+void format_range(int64_t r0, int64_t r1, int32_t cols, const char *names, const int64_t *name_off, Get get, Sink *out)
 {
-    out->reserve((size_t)(r1 - r0) * ((size_t)cols * 8 + 32));
     for (int64_t r = r0; r < r1; ++r) {
         if (names) {       // f"{name}\t{tab.join(values)}\n": the tab is there even without values
             out->append(names + name_off[r], (size_t)(name_off[r + 1] - name_off[r]));
@@ -132,6 +171,61 @@ void format_range(int64_t r0, int64_t r1, int32_t cols, const char *names, const
     }
 }
 
+// Formats rows [0, rows) on n_threads threads, thread t writing its row range into the slice
+// [cap * r0 / rows, cap * r1 / rows) of `out`.  seg_off / seg_len receive each thread's text;
+// returns the number of bytes that did not fit (0 = complete).
+size_t format_segments(int kind, const void *matrix, int64_t rows, int32_t cols, int64_t ld, const char *names,
+                       const int64_t *name_off, char *out, size_t cap, int n_threads, size_t *seg_off, size_t *seg_len)
+{
+    std::vector<size_t> dropped((size_t)n_threads, 0);
+    auto work = [&](int t) {
+        const int64_t r0 = rows * t / n_threads, r1 = rows * (t + 1) / n_threads;
+        const size_t b0 = (size_t)((long double)cap * r0 / rows), b1 = (size_t)((long double)cap * r1 / rows);
+        Sink sink(out ? out + b0 : nullptr, out ? out + b1 : nullptr);
+        if (kind == 0) {
+            const float *m = static_cast<const float *>(matrix);
+            format_range(r0, r1, cols, names, name_off,
+                         [m, ld](Sink &s, int64_t r, int32_t c) { put_value_f(s, (double)m[r * ld + c]); }, &sink);
+        } else if (kind == 1) {
+            const double *m = static_cast<const double *>(matrix);
+            format_range(r0, r1, cols, names, name_off,
+                         [m, ld](Sink &s, int64_t r, int32_t c) { put_value_f(s, m[r * ld + c]); }, &sink);
+        } else if (kind == 3) {
+            const double *m = static_cast<const double *>(matrix);
+            format_range(r0, r1, cols, names, name_off,
+                         [m, ld](Sink &s, int64_t r, int32_t c) { put_repr(s, m[r * ld + c]); }, &sink);
+        } else {
+            const int32_t *m = static_cast<const int32_t *>(matrix);
+            format_range(r0, r1, cols, names, name_off,
+                         [m, ld](Sink &s, int64_t r, int32_t c) {
+                             const int64_t v = m[r * ld + c];
+                             if (v < 0) s.push_back('-');
+                             put_uint(s, (uint64_t)(v < 0 ? -v : v));
+                         },
+                         &sink);
+        }
+        seg_off[t] = b0;
+        seg_len[t] = out ? (size_t)(sink.p - (out + b0)) : 0;
+        dropped[t] = sink.dropped;
+    };
+    if (n_threads == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < n_threads; ++t) pool.emplace_back(work, t);
+        for (auto &th : pool) th.join();
+    }
+    size_t lost = 0;
+    for (size_t d : dropped) lost += d;
+    return lost;
+}
+
+int pick_threads(int n_threads, int64_t rows)
+{
+    if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    return (int)std::min<int64_t>(n_threads, std::max<int64_t>(1, rows / 64));
+}
+
 }  // namespace
 
 extern "C" int sd_host_format_rows(int kind, const void *matrix, int64_t rows, int32_t cols, int64_t ld,
@@ -142,51 +236,60 @@ extern "C" int sd_host_format_rows(int kind, const void *matrix, int64_t rows, i
                "sd_host_format_rows: kind must be 0 (f32 %%.3f), 1 (f64 %%.3f), 2 (i32) or 3 (f64 repr)");
     SD_REQUIRE(rows >= 0 && cols >= 0 && ld >= cols && written, "sd_host_format_rows: bad shape");
     SD_REQUIRE((rows == 0 || cols == 0 || matrix) && (!names || name_off), "sd_host_format_rows: null pointer");
-    if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
-    n_threads = (int)std::min<int64_t>(n_threads, std::max<int64_t>(1, rows / 64));
-    std::vector<std::string> parts((size_t)n_threads);
-    auto work = [&](int t) {
-        const int64_t r0 = rows * t / n_threads, r1 = rows * (t + 1) / n_threads;
-        if (kind == 0) {
-            const float *m = static_cast<const float *>(matrix);
-            format_range(r0, r1, cols, names, name_off,
-                         [m, ld](std::string &s, int64_t r, int32_t c) { put_value_f(s, (double)m[r * ld + c]); }, &parts[t]);
-        } else if (kind == 1) {
-            const double *m = static_cast<const double *>(matrix);
-            format_range(r0, r1, cols, names, name_off,
-                         [m, ld](std::string &s, int64_t r, int32_t c) { put_value_f(s, m[r * ld + c]); }, &parts[t]);
-        } else if (kind == 3) {
-            const double *m = static_cast<const double *>(matrix);
-            format_range(r0, r1, cols, names, name_off,
-                         [m, ld](std::string &s, int64_t r, int32_t c) { put_repr(s, m[r * ld + c]); }, &parts[t]);
-        } else {
-            const int32_t *m = static_cast<const int32_t *>(matrix);
-            format_range(r0, r1, cols, names, name_off,
-                         [m, ld](std::string &s, int64_t r, int32_t c) {
-                             const int64_t v = m[r * ld + c];
-                             if (v < 0) s.push_back('-');
-                             put_uint(s, (uint64_t)(v < 0 ? -v : v));
-                         },
-                         &parts[t]);
-        }
-    };
-    if (n_threads == 1) {
-        work(0);
-    } else {
-        std::vector<std::thread> pool;
-        for (int t = 0; t < n_threads; ++t) pool.emplace_back(work, t);
-        for (auto &th : pool) th.join();
-    }
+    *written = 0;
+    if (rows == 0) return SD_OK;
+    n_threads = pick_threads(n_threads, rows);
+    std::vector<size_t> off((size_t)n_threads), len((size_t)n_threads);
+    const size_t lost = format_segments(kind, matrix, rows, cols, ld, names, name_off, out, out ? cap : 0, n_threads,
+                                        off.data(), len.data());
     size_t total = 0;
-    for (auto &p : parts) total += p.size();
-    *written = total;
-    if (total > cap || (!out && total))
-        return sd::fail(SD_ERR_WORKSPACE, "sd_host_format_rows: %zu bytes needed, %zu given", total, cap);
-    size_t off = 0;
-    for (auto &p : parts) {
-        memcpy(out + off, p.data(), p.size());
-        off += p.size();
+    for (size_t l : len) total += l;
+    if (lost) {
+        // the slices are proportional to the row counts, so ask for the worst slice's ratio everywhere
+        *written = (total + lost) * 2 + 4096;
+        return sd::fail(SD_ERR_WORKSPACE, "sd_host_format_rows: about %zu bytes needed, %zu given", *written, cap);
     }
+    // close the gaps between the threads' slices (every move goes towards the front, in order)
+    size_t pos = 0;
+    for (int t = 0; t < n_threads; ++t) {
+        if (off[t] != pos) memmove(out + pos, out + off[t], len[t]);
+        pos += len[t];
+    }
+    *written = total;
+    return SD_OK;
+}
+
+// As sd_host_format_rows, but the text stays where each thread wrote it: segment k is
+// out[seg_off[k], seg_off[k] + seg_len[k]), k < *n_segments <= max_segments, to be written out in
+// order (the writers stream row chunks to a file this way without compacting or copying).
+extern "C" int sd_host_format_rows_segments(int kind, const void *matrix, int64_t rows, int32_t cols, int64_t ld,
+                                            const char *names, const int64_t *name_off, char *out, size_t cap,
+                                            int64_t *seg_off, int64_t *seg_len, int32_t max_segments,
+                                            int32_t *n_segments, size_t *needed, int n_threads)
+{
+    SD_REQUIRE(kind >= 0 && kind <= 3, "sd_host_format_rows_segments: kind must be 0..3");
+    SD_REQUIRE(rows >= 0 && cols >= 0 && ld >= cols && seg_off && seg_len && n_segments && needed && max_segments >= 1,
+               "sd_host_format_rows_segments: bad arguments");
+    SD_REQUIRE((rows == 0 || ((cols == 0 || matrix) && out)) && (!names || name_off),
+               "sd_host_format_rows_segments: null pointer");
+    *n_segments = 0;
+    *needed = 0;
+    if (rows == 0) return SD_OK;
+    n_threads = std::min(pick_threads(n_threads, rows), (int)max_segments);
+    std::vector<size_t> off((size_t)n_threads), len((size_t)n_threads);
+    const size_t lost = format_segments(kind, matrix, rows, cols, ld, names, name_off, out, cap, n_threads, off.data(),
+                                        len.data());
+    if (lost) {
+        size_t total = 0;
+        for (size_t l : len) total += l;
+        *needed = (total + lost) * 2 + 4096;
+        return sd::fail(SD_ERR_WORKSPACE, "sd_host_format_rows_segments: about %zu bytes needed, %zu given", *needed, cap);
+    }
+    for (int t = 0; t < n_threads; ++t) {
+        seg_off[t] = (int64_t)off[t];
+        seg_len[t] = (int64_t)len[t];
+    }
+    *n_segments = n_threads;
     return SD_OK;
 }
 

@@ -76,6 +76,8 @@ _SIGNATURES = {
     "sd_ingest_counts": (c_int, [_P, c_int32, _P, _P, _P, _P, _P, c_int64, _P, c_int64, c_int32]),
     "sd_host_format_rows": (c_int, [c_int, _P, c_int64, c_int32, c_int64, _P, _P, _P, c_size_t,
                                     POINTER(c_size_t), c_int]),
+    "sd_host_format_rows_segments": (c_int, [c_int, _P, c_int64, c_int32, c_int64, _P, _P, _P, c_size_t, _P, _P, c_int32,
+                                             POINTER(c_int32), POINTER(c_size_t), c_int]),
     "sd_synth_counts": (c_int, [c_uint64, c_int64, c_int64, c_int32, c_int64, c_uint32, _P, c_int64, _P]),
     "sd_probe_fp64": (c_int, [POINTER(c_double), _P]),
     "sd_probe_copy": (c_int, [c_int64, POINTER(c_double), _P]),

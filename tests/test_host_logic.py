@@ -162,6 +162,40 @@ def test_pairwise_value_formatter_matches_str():
     assert textio.format_rows(y, repr_floats=True) == want.encode()
 
 
+def test_write_matrix_streams_segments_byte_identically(tmp_path):
+    """write_matrix (sd_host_format_rows_segments: per-thread slices written in order, no
+    compaction) produces the same file as the one-shot formatter, for every chunking / thread
+    count, including a buffer that starts too small and rows of very uneven text length."""
+    import ctypes
+    from splicedice_b200 import native, textio
+    rng = np.random.default_rng(5)
+    x = rng.random((3000, 37))
+    x[:1500] *= 1e11                                  # first half ~15 bytes per cell, second half 5
+    names = [f"chrX:{i}-{i * 3 + 7}:-" for i in range(3000)]
+    want = b"h\tcols\n" + textio.format_rows(x, names)
+    for chunk, threads in ((None, 0), (7, 3), (1000, 1), (2999, 8)):
+        path = tmp_path / f"m_{chunk}_{threads}.tsv"
+        textio.write_matrix(str(path), "h\tcols\n", names, x, chunk_rows=chunk, threads=threads)
+        assert path.read_bytes() == want
+    p = rng.random((500, 20)) * 10.0 ** rng.integers(-300, 0, (500, 20))
+    path = tmp_path / "p.tsv"
+    textio.write_matrix(str(path), "", None, p, repr_floats=True, chunk_rows=128)
+    assert path.read_bytes() == textio.format_rows(p, repr_floats=True)
+    textio.write_matrix(str(path), "only header\n", [], np.zeros((0, 4), dtype=np.float32))
+    assert path.read_bytes() == b"only header\n"
+    # too-small buffer: SD_ERR_WORKSPACE and a sufficient size, never an overrun
+    lib = native.load()
+    m, blob, off = textio._prepare(x, names, False)
+    buf = np.full(4096 + 64, 0x55, dtype=np.uint8)
+    so, sl = np.empty(8, dtype=np.int64), np.empty(8, dtype=np.int64)
+    ns, need = ctypes.c_int32(), ctypes.c_size_t()
+    rc = lib.sd_host_format_rows_segments(1, native.ptr(m), 3000, 37, 37, blob, native.ptr(off), native.ptr(buf), 4096,
+                                          native.ptr(so), native.ptr(sl), 8, ctypes.byref(ns), ctypes.byref(need), 4)
+    assert rc == native.SD_ERR_WORKSPACE and need.value >= len(want) - 7 and (buf[4096:] == 0x55).all()
+    buf, segs = textio._format_segments(m, blob, off, 4, False, np.empty(4096, dtype=np.uint8))
+    assert b"".join(bytes(buf[o:o + n]) for o, n in segs) == want[7:]
+
+
 def _quant_job(manifest, out, extra=(), native_io=True):
     import argparse
     from splicedice_b200 import quant
