@@ -87,27 +87,40 @@ def _format_segments(m, blob, off, threads, repr_floats, buf):
 
 def write_matrix(path, header: str, names, matrix, chunk_rows=None, threads=0, repr_floats=False):
     """header line + one formatted row per junction, streamed in row chunks of ~64 MB of text
-    through one reusable buffer (formatted natively; each formatter thread's slice goes to the
-    file from where it was written, no compaction and no python-side copy)."""
+    through two alternating buffers: chunk k is written by a helper thread while chunk k+1 is
+    being formatted (both release the GIL).  Each formatter thread's slice goes to the file from
+    where it was written — no compaction, no python-side copy."""
+    from concurrent.futures import ThreadPoolExecutor
     m = np.asarray(matrix)
     cols = m.shape[1] if m.ndim == 2 else 0
     if chunk_rows is None:
         chunk_rows = max(1, min(65536, (64 << 20) // max(1, cols * _cell_bytes(repr_floats) + 40)))
-    buf = None
-    with open(path, "wb") as out:
+    bufs = [None, None]
+
+    def flush(out, buf, segments):
+        view = memoryview(buf)
+        for o, n in segments:
+            out.write(view[o:o + n])
+
+    with open(path, "wb") as out, ThreadPoolExecutor(1) as writer:
         out.write(header.encode())
-        for r0 in range(0, m.shape[0], chunk_rows):
+        pending = [None, None]
+        for k, r0 in enumerate(range(0, m.shape[0], chunk_rows)):
             part, blob, off = _prepare(m[r0:r0 + chunk_rows], None if names is None else names[r0:r0 + chunk_rows],
                                        repr_floats)
             if part.shape[0] == 0:
                 continue
+            slot = k & 1
+            if pending[slot] is not None:
+                pending[slot].result()               # this buffer's previous text is on its way to the file
             cap = part.shape[0] * (cols * _cell_bytes(repr_floats) + 40) + (len(blob) if blob else 0) + 64
-            if buf is None or buf.size < cap:
-                buf = np.empty(cap, dtype=np.uint8)
-            buf, segments = _format_segments(part, blob, off, threads, repr_floats, buf)
-            view = memoryview(buf)
-            for o, n in segments:
-                out.write(view[o:o + n])
+            if bufs[slot] is None or bufs[slot].size < cap:
+                bufs[slot] = np.empty(cap, dtype=np.uint8)
+            bufs[slot], segments = _format_segments(part, blob, off, threads, repr_floats, bufs[slot])
+            pending[slot] = writer.submit(flush, out, bufs[slot], segments)   # one writer thread: chunks stay in order
+        for f in pending:
+            if f is not None:
+                f.result()
 
 
 def read_table(path, threads=0):
