@@ -107,6 +107,7 @@ int sd_cluster_fill(int64_t n_junctions, int64_t nnz, const int32_t *row_of_pos,
 #define SD_QUANT_TILED 2u         /* TMA-staged shared-memory tile kernel (aligned inputs) */
 #define SD_QUANT_VARIANT_MASK 0xFFu
 /* bits 8..15: log2(rows per tile) override (tuning / tests) */
+#define SD_QUANT_ROWS(n) (((uint32_t)(n) & 0xFFu) << 24)   /* wide kernel: n rows per tile, 8..128 (tuning / tests) */
 #define SD_QUANT_VEC1 0x20000u           /* wide kernel: 128-column slabs (4 columns per lane) */
 #define SD_QUANT_VEC2 0x40000u           /* wide kernel: 256-column slabs (8 columns per lane) */
 #define SD_QUANT_NARROW_TILES 0x10000u   /* force the narrow-matrix tile kernel for any n_samples (tests) */

@@ -155,10 +155,13 @@ def test_small_divide_exhaustive_and_random():
     np.testing.assert_array_equal(util.bits32(general), util.bits32(want))
 
 
-@pytest.mark.parametrize("log_r", [3, 5, 7])
+@pytest.mark.parametrize("log_r", [3, 5, 7, -24, -48, -100])
 def test_wide_kernel_tile_shapes_and_unstaged_adjacency(log_r):
-    """Deep nests (adjacency of one tile larger than the staging buffer) and other tile heights."""
+    """Deep nests (adjacency of one tile larger than the staging buffer) and other tile heights
+    (negative: SD_QUANT_ROWS(n), tile heights that are not powers of two -- 48 is what large
+    matrices get by default)."""
     native, ops = _ops()
+    tile_flag = (log_r << 8) if log_r > 0 else ((-log_r) << 24)
     from splicedice_b200 import synth
     js = [("chr1", 1000, 900000, "+")] + [("chr1", 2000 + 40 * i, 2030 + 40 * i, "+") for i in range(3000)]
     js += synth.junction_tuples(2000, 5)
@@ -168,13 +171,13 @@ def test_wide_kernel_tile_shapes_and_unstaged_adjacency(log_r):
     counts = synth.counts_host(3, 0, J, S)
     dev = torch.device("cuda", 0)
     r = ops.quant_ps(torch.from_numpy(counts).to(dev), csr["row_ptr"], csr["col_idx"], want_exc=True,
-                     flags=native.SD_QUANT_TILED | (log_r << 8))
+                     flags=native.SD_QUANT_TILED | tile_flag)
     exc = oracle_np.exclusion_sums(counts, csr["row_ptr"], csr["col_idx"])
     np.testing.assert_array_equal(r["exc"].cpu().numpy(), exc)
     want = oracle_np.ps_f32(counts, csr["row_ptr"], csr["col_idx"], exc=exc)
     np.testing.assert_array_equal(util.bits32(r["ps_f32"].cpu().numpy()), util.bits32(want))
     lean = ops.quant_ps(torch.from_numpy(counts).to(dev), csr["row_ptr"], csr["col_idx"],
-                        flags=native.SD_QUANT_TILED | (log_r << 8))["ps_f32"].cpu().numpy()
+                        flags=native.SD_QUANT_TILED | tile_flag)["ps_f32"].cpu().numpy()
     np.testing.assert_array_equal(util.bits32(lean), util.bits32(want))
 
 

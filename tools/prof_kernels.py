@@ -25,6 +25,18 @@ def main():
         cl = ops.cluster_build(*synth.junction_arrays(J, 20261018)[:4])
         counts = ops.synth_counts(1, 0, J, S, device=dev)
         ps = torch.empty((J, S), dtype=torch.float32, device=dev)
+        if os.environ.get("SD_PROF_EMPTY_CSR"):           # structural floor: no neighbours at all
+            cl["row_ptr"].zero_()
+        if os.environ.get("SD_PROF_INTILE_ONLY"):         # drop every neighbour outside its row's R-row tile
+            R = int(os.environ["SD_PROF_INTILE_ONLY"])
+            rp, ci = cl["row_ptr"].cpu().numpy(), cl["col_idx"].cpu().numpy()
+            rows = np.repeat(np.arange(J), np.diff(rp))
+            keep = (rows // R) == (ci // R)
+            print(f"  in-tile entries: {keep.mean():.3f} of {len(ci)}")
+            rp2 = np.zeros(J + 1, dtype=np.int32)
+            np.cumsum(np.bincount(rows[keep], minlength=J), out=rp2[1:])
+            cl["row_ptr"] = torch.from_numpy(rp2).to(dev)
+            cl["col_idx"] = torch.from_numpy(ci[keep].astype(np.int32)).to(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for i in range(4):
             if i == 1:
