@@ -588,7 +588,7 @@ def main():
                        "l2": f"inputs+outputs {cells_rank * 8 / 1e9:.1f} GB per pass per GPU >> 126 MB L2, no flush", "seed": SEED,
                        "cluster_build_ms": t_k1 * 1e3, "flags": args.flags},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "traffic_source": traffic_src, "kernel": "quant_wide_kernel<2, true>", "kernel_ms": kernel_ms,
+                         "traffic": traffic, "traffic_source": traffic_src, "kernel": "quant_wide_kernel<2, kOutF32> (256-column slabs, 48-row TMA tiles)", "kernel_ms": kernel_ms,
                          "bytes_per_cell": 8, "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps, "launch_mode": "cuda graph of K kernel launches" if graph is not None else "K stream launches",
             "clocks": clocks, "variants": variants, "fisher": fisher,
