@@ -178,10 +178,15 @@ struct GroupBins {
 };
 static_assert(sizeof(GroupBins) % 16 == 0, "GroupBins must keep 16-byte alignment between groups");
 
-template <int kMode, int kSub, bool kStaged>
+// kPre (needs kStaged): the per-sample halves of every table's log-factorial sums
+// (fisher::SampleTerms: lg[inc] + lg[exc] and log C(inc + exc, inc), 32 bytes per sample) are
+// computed once per (junction, sample) while the row is staged and kept in shared memory behind
+// the GroupBins, so a table needs 9 compensated additions and 7 table look-ups instead of 16
+// and 21.  Used whenever the staged table leaves room for kSub * n_samples of them.
+template <int kMode, int kSub, bool kStaged, bool kPre>
 __global__ void __launch_bounds__(kFisherThreads *kSub, 1) fisher_pairwise_binned_kernel(const FisherParams p)
 {
-    // dynamic shared memory: the staged table, then one GroupBins per 256-thread group
+    // dynamic shared memory: the staged table, one GroupBins per 256-thread group, the per-sample terms
     extern __shared__ __align__(16) double2 s_tab[];
     stage_table(s_tab, p.table, p.smem_entries);
     const DeviceTable<kMode> tab{smem_u32(s_tab), p.table, p.smem_entries, p.table_entries};
@@ -189,6 +194,9 @@ __global__ void __launch_bounds__(kFisherThreads *kSub, 1) fisher_pairwise_binne
     const int group = (int)(threadIdx.x / kFisherThreads);
     const int tid = (int)(threadIdx.x % kFisherThreads), lane = tid & 31;
     GroupBins &bins = reinterpret_cast<GroupBins *>(s_tab + p.smem_entries)[group];
+    fisher::SampleTerms *s_pre =
+        reinterpret_cast<fisher::SampleTerms *>(reinterpret_cast<GroupBins *>(s_tab + p.smem_entries) + kSub) +
+        (size_t)group * p.n_samples;
     uint16_t *s_perm = bins.perm, *s_rank = bins.rank;
     uint8_t *s_key = bins.key;
     int *s_hist = bins.hist, *s_base = bins.base, *s_next = &bins.next;
@@ -224,6 +232,7 @@ __global__ void __launch_bounds__(kFisherThreads *kSub, 1) fisher_pairwise_binne
                 const bool bad = ia < 0 || ea < 0 || ia + ea > p.cell_bound;
                 s_inc[sm] = bad ? -1 : ia;
                 s_exc[sm] = bad ? -1 : (int32_t)ea;
+                if (kPre && !bad) s_pre[sm] = fisher::sample_terms(tab, ia, (int32_t)ea);
             }
         }
         group_sync(group);
@@ -263,12 +272,21 @@ __global__ void __launch_bounds__(kFisherThreads *kSub, 1) fisher_pairwise_binne
             if (slot < cnt) {
                 const int64_t k = k0 + s_perm[slot];
                 int a, b, c, d;
-                cells(inc, exc, k, a, b, c, d);
                 double pv;
-                if (a < 0)
-                    pv = __longlong_as_double(0x7FF8000000000000ll);      // outside the promised range: loud, not wrong
-                else
-                    pv = fisher::two_sided<int32_t>(tab, a, b, c, d);
+                if (kPre) {
+                    const int sa = __ldg(p.pair_a + k), sb = __ldg(p.pair_b + k);
+                    a = s_inc[sa] | s_inc[sb]; b = s_inc[sb]; c = s_exc[sa]; d = s_exc[sb];
+                    if (a < 0)
+                        pv = __longlong_as_double(0x7FF8000000000000ll);  // outside the promised range: loud, not wrong
+                    else
+                        pv = fisher::two_sided_pre<int32_t>(tab, s_inc[sa], b, c, d, s_pre[sa], s_pre[sb]);
+                } else {
+                    cells(inc, exc, k, a, b, c, d);
+                    if (a < 0)
+                        pv = __longlong_as_double(0x7FF8000000000000ll);
+                    else
+                        pv = fisher::two_sided<int32_t>(tab, a, b, c, d);
+                }
                 p.p_out[j * p.ld_p + k] = pv;
             }
         }
@@ -421,10 +439,14 @@ struct PairwiseLauncher {
     template <int kSub, bool kStaged>
     static int launch_binned(const FisherParams &p, cudaStream_t stream)
     {
-        auto kernel = fisher_pairwise_binned_kernel<kMode, kSub, kStaged>;
-        const size_t smem = (size_t)p.smem_entries * sizeof(double2) + kSub * sizeof(GroupBins);
-        SD_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)(kSmemEntriesBinned * sizeof(double2) + kSub * sizeof(GroupBins))));
+        constexpr size_t kMaxSmem = kSmemEntriesBinned * sizeof(double2) + kSub * sizeof(GroupBins);
+        const size_t base = (size_t)p.smem_entries * sizeof(double2) + kSub * sizeof(GroupBins);
+        const size_t pre = (size_t)kSub * p.n_samples * sizeof(fisher::SampleTerms);
+        const bool use_pre = kStaged && base + pre <= kMaxSmem && !getenv("SD_FISHER_NO_PRE");
+        auto kernel = use_pre ? fisher_pairwise_binned_kernel<kMode, kSub, kStaged, kStaged>
+                              : fisher_pairwise_binned_kernel<kMode, kSub, kStaged, false>;
+        const size_t smem = base + (use_pre ? pre : 0);
+        SD_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
         const int64_t items = (p.row_end - p.row_begin) * ((p.n_pairs + kBinChunk - 1) / kBinChunk);
         int grid = fisher_grid((const void *)kernel, smem, kFisherThreads * kSub);
         grid = (int)std::min<int64_t>(grid, (items + kSub - 1) / kSub);

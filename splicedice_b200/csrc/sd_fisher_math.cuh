@@ -213,22 +213,42 @@ SD_HD dd acc_result(double sum, double err)
     return dd_make(hi, err - (hi - sum));
 }
 
-// f(x) = log(pmf(x) / pmf(a)) in double-double: G(a) - G(x) as one compensated sum of the eight
-// table entries (TwoSum on the hi words, rounding errors and lo words accumulated separately --
-// the error words are ~1e-12, so their plain-double sum is good to ~1e-27).  Out of line, with
-// everything passed by value, so the call does not force the caller's state into local memory.
+// Per-sample terms of a table column (inc, exc): both depend on one sample only, so the pairwise
+// kernel computes them once per (junction, sample) instead of once per pair.  Kept as unnormalised
+// (sum, err) pairs of a compensated sum -- TwoSum on the hi words, rounding errors and lo words
+// accumulated in err:
+//   g = lg[inc] + lg[exc]                 (this column's half of G(a))
+//   c = lg[inc + exc] - lg[inc] - lg[exc] (log of the binomial coefficient C(inc + exc, inc))
+struct SampleTerms {
+    double g_sum, g_err, c_sum, c_err;
+};
+
 template <class Table, class Int>
-SD_NOINLINE dd f_exact_of(Table tab, Int a, Int b, Int c, Int d, Int n1, Int n2, Int n, Int x)
+SD_HD SampleTerms sample_terms(const Table &tab, Int inc, Int exc)
 {
-    const dd t0 = tab.get(a), t1 = tab.get(x), t2 = tab.get(b), t3 = tab.get(n1 - x);
-    const dd t4 = tab.get(c), t5 = tab.get(n - x), t6 = tab.get(d), t7 = tab.get(n2 - n + x);
-    double sum = t0.hi, err = t0.lo;
+    const dd ti = tab.get(inc), te = tab.get(exc), tn = tab.get(inc + exc);
+    SampleTerms t;
+    t.g_sum = ti.hi; t.g_err = ti.lo;
+    acc_two_sum(t.g_sum, t.g_err, te.hi, te.lo);
+    t.c_sum = tn.hi; t.c_err = tn.lo;
+    acc_two_sum(t.c_sum, t.c_err, -ti.hi, -ti.lo);
+    acc_two_sum(t.c_sum, t.c_err, -te.hi, -te.lo);
+    return t;
+}
+
+// f(x) = log(pmf(x) / pmf(a)) in double-double: G(a) - G(x) as one compensated sum -- G(a) comes
+// in as its (sum, err) pair, the four table entries of G(x) are subtracted with TwoSum on the hi
+// words, rounding errors and lo words accumulated separately (the error words are ~1e-12, so
+// their plain-double sum is good to ~1e-27).  Out of line, with everything passed by value, so
+// the call does not force the caller's state into local memory.
+template <class Table, class Int>
+SD_NOINLINE dd f_exact_of(Table tab, double ga_sum, double ga_err, Int n1, Int n2, Int n, Int x)
+{
+    const dd t1 = tab.get(x), t3 = tab.get(n1 - x), t5 = tab.get(n - x), t7 = tab.get(n2 - n + x);
+    double sum = ga_sum, err = ga_err;
     acc_two_sum(sum, err, -t1.hi, -t1.lo);
-    acc_two_sum(sum, err, t2.hi, t2.lo);
     acc_two_sum(sum, err, -t3.hi, -t3.lo);
-    acc_two_sum(sum, err, t4.hi, t4.lo);
     acc_two_sum(sum, err, -t5.hi, -t5.lo);
-    acc_two_sum(sum, err, t6.hi, t6.lo);
     acc_two_sum(sum, err, -t7.hi, -t7.lo);
     return acc_result(sum, err);
 }
@@ -239,17 +259,16 @@ template <class Table, class Int>
 struct Problem {
     const Table &tab;
     Int n1, n2, n;
-    Int a, b, c, d;
+    double ga_sum, ga_err;   // G(a) = lg[a] + lg[b] + lg[c] + lg[d] as a compensated (sum, err) pair
     double tol;   // bound on the error of a hi-only evaluation of G(a) - G(x)
-    double Ga;    // G(a) from the hi words, computed once (every probe of the search needs it)
 
     // f(x) = log(pmf(x) / pmf(a)) from the hi words only: at most seven roundings of at most
     // eps/2 * lg[N] each (every partial sum is below lg[N]), well inside `tol`
     SD_HD double f_fast(Int x) const
     {
-        return Ga - ((tab.hi(x) + tab.hi(n1 - x)) + (tab.hi(n - x) + tab.hi(n2 - n + x)));
+        return ga_sum - ((tab.hi(x) + tab.hi(n1 - x)) + (tab.hi(n - x) + tab.hi(n2 - n + x)));
     }
-    SD_HD dd f_exact(Int x) const { return f_exact_of<Table, Int>(tab, a, b, c, d, n1, n2, n, x); }
+    SD_HD dd f_exact(Int x) const { return f_exact_of<Table, Int>(tab, ga_sum, ga_err, n1, n2, n, x); }
     // scipy's far-side admission test: pmf(x) <= pexact * (1 + 1e-14)
     SD_HD bool admitted(Int x) const
     {
@@ -273,8 +292,9 @@ struct Plan {
     Int total;              // N, decides which tail-sum routine is exact
 };
 
+// ta / tb: sample_terms of the table's two columns, (a, c) and (b, d)
 template <class Int, class Table>
-SD_HD Plan<Int> make_plan(const Table &tab, Int a, Int b, Int c, Int d)
+SD_HD Plan<Int> make_plan_pre(const Table &tab, Int a, Int b, Int c, Int d, const SampleTerms &ta, const SampleTerms &tb)
 {
     Plan<Int> pl;
     pl.known = true; pl.pexact = 1.0; pl.tg = 0.0; pl.total = 0;
@@ -289,7 +309,8 @@ SD_HD Plan<Int> make_plan(const Table &tab, Int a, Int b, Int c, Int d)
     // Observed count above the mode: swap the columns.  x -> n1 - x maps the distribution onto
     // hypergeom(N, n1, N - n) with identical pmf values, so from here on a < mode and the far
     // side is the upper one.  (The reflected mode is only used as a point whose pmf exceeds
-    // pmf(a) * (1 + 1e-14), which the tie test below guarantees.)
+    // pmf(a) * (1 + 1e-14), which the tie test below guarantees.)  Everything taken from ta / tb
+    // is symmetric in the two columns.
     if (a > mode) {
         Int t = a; a = b; b = t;
         t = c; c = d; d = t;
@@ -298,9 +319,9 @@ SD_HD Plan<Int> make_plan(const Table &tab, Int a, Int b, Int c, Int d)
     }
     const Int hi = n1 < n ? n1 : n;
 
-    Problem<Table, Int> pr{tab, n1, n2, n, a, b, c, d, 0.0, 0.0};
+    Problem<Table, Int> pr{tab, n1, n2, n, ta.g_sum, ta.g_err, 0.0};
+    acc_two_sum(pr.ga_sum, pr.ga_err, tb.g_sum, tb.g_err);
     pr.tol = 64.0 * 2.220446049250313e-16 * (tab.hi(N) + 1.0);
-    pr.Ga = (tab.hi(a) + tab.hi(b)) + (tab.hi(c) + tab.hi(d));
 
     // tie between the observed table and the mode (plateau or mirror twin)
     {
@@ -311,21 +332,16 @@ SD_HD Plan<Int> make_plan(const Table &tab, Int a, Int b, Int c, Int d)
         }
     }
 
-    // log pmf(a): compensated sum of the nine table entries (TwoSum on the hi words, the
-    // rounding errors and lo words accumulated separately)
+    // log pmf(a) = lg[n1] + lg[n2] - lg[N] + log C(a + c, a) + log C(b + d, b): compensated sum
+    // of three table entries and the two per-sample terms
     double lp_hi, lp_lo;
     {
-        const dd t0 = tab.get(n1), t1 = tab.get(n2), t2 = tab.get(n), t3 = tab.get(N - n), t4 = tab.get(N);
-        const dd t5 = tab.get(a), t6 = tab.get(b), t7 = tab.get(c), t8 = tab.get(d);
+        const dd t0 = tab.get(n1), t1 = tab.get(n2), t4 = tab.get(N);
         double sum = t0.hi, err = t0.lo;
         acc_two_sum(sum, err, t1.hi, t1.lo);
-        acc_two_sum(sum, err, t2.hi, t2.lo);
-        acc_two_sum(sum, err, t3.hi, t3.lo);
         acc_two_sum(sum, err, -t4.hi, -t4.lo);
-        acc_two_sum(sum, err, -t5.hi, -t5.lo);
-        acc_two_sum(sum, err, -t6.hi, -t6.lo);
-        acc_two_sum(sum, err, -t7.hi, -t7.lo);
-        acc_two_sum(sum, err, -t8.hi, -t8.lo);
+        acc_two_sum(sum, err, ta.c_sum, ta.c_err);
+        acc_two_sum(sum, err, tb.c_sum, tb.c_err);
         lp_hi = sum + err;
         lp_lo = err - (lp_hi - sum);
     }
@@ -370,9 +386,14 @@ SD_HD Plan<Int> make_plan(const Table &tab, Int a, Int b, Int c, Int d)
 }
 
 template <class Int, class Table>
-SD_HD double two_sided(const Table &tab, Int a, Int b, Int c, Int d)
+SD_HD Plan<Int> make_plan(const Table &tab, Int a, Int b, Int c, Int d)
 {
-    const Plan<Int> pl = make_plan<Int>(tab, a, b, c, d);
+    return make_plan_pre<Int>(tab, a, b, c, d, sample_terms(tab, a, c), sample_terms(tab, b, d));
+}
+
+template <class Int>
+SD_HD double plan_value(const Plan<Int> &pl)
+{
     if (pl.known) return pl.pexact;
     double rel;
     if ((int64_t)pl.total < (int64_t(1) << 26)) {
@@ -386,6 +407,19 @@ SD_HD double two_sided(const Table &tab, Int a, Int b, Int c, Int d)
     }
     const double p = pl.pexact * rel;
     return p > 1.0 ? 1.0 : p;
+}
+
+template <class Int, class Table>
+SD_HD double two_sided(const Table &tab, Int a, Int b, Int c, Int d)
+{
+    return plan_value(make_plan<Int>(tab, a, b, c, d));
+}
+
+// the pairwise kernel's form: the columns' per-sample terms were computed once per junction
+template <class Int, class Table>
+SD_HD double two_sided_pre(const Table &tab, Int a, Int b, Int c, Int d, const SampleTerms &ta, const SampleTerms &tb)
+{
+    return plan_value(make_plan_pre<Int>(tab, a, b, c, d, ta, tb));
 }
 
 // hypergeometric support size of a table (0 for a zero-margin table): the work unit of the
