@@ -153,7 +153,14 @@ SD_HD double tail_fast(double p, double q, double u, double v)
 {
     TailState t;
     t.init(p, q, u, v);
+    // The cut is tested every four terms, the rescale only every eight: a step multiplies Q by
+    // less than 2^52 (totals below 2^26), so from below 2^500 eight steps stay under 2^916.
     do {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+        for (int i = 0; i < 4; ++i) t.step();
+        if (t.done()) break;
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif

@@ -151,6 +151,26 @@ def test_kernel_instantiations_agree():
     finally:
         del os.environ["SD_FISHER_PLAIN"]
     _check(got.ravel(), want.ravel(), rtol=1e-11)
+    # per-sample log-factorial terms staged once per junction (the default whenever they fit next
+    # to the table) against the same arithmetic evaluated per pair: identical bits; a table that
+    # fills shared memory (bound 5,000 -> 10,001 entries) leaves no room for 400 samples' terms
+    staged = ops.fisher_pairwise(inc_d, exc_d, pa, pb).cpu().numpy()
+    os.environ["SD_FISHER_NO_PRE"] = "1"
+    try:
+        per_pair = ops.fisher_pairwise(inc_d, exc_d, pa, pb).cpu().numpy()
+    finally:
+        del os.environ["SD_FISHER_NO_PRE"]
+    np.testing.assert_array_equal(staged.view(np.uint64), per_pair.view(np.uint64))
+    J3, S3 = 30, 400
+    _, csr3, counts3 = util.synthetic_problem(J3, S3, seed=35, zero_frac=0.05)
+    exc3 = oracle_np.exclusion_sums(counts3, csr3["row_ptr"], csr3["col_idx"])
+    qa3, qb3 = oracle_np.all_pairs(S3)
+    qa3, qb3 = qa3[::37], qb3[::37]
+    want3 = fisher_c.pairwise(counts3, exc3, qa3, qb3)
+    for bound in (int((counts3 + exc3).max()), 5_000):
+        got3 = ops.fisher_pairwise(torch.from_numpy(counts3).to(dev), torch.from_numpy(exc3).to(dev), qa3, qb3,
+                                   max_cell_bound=bound).cpu().numpy()
+        _check(got3.ravel(), want3.ravel(), rtol=1e-11)
 
     # 600 samples (> 512: unstaged row), an arbitrary pair list with repeats and a == b
     J2, S2 = 40, 600
