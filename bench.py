@@ -499,14 +499,14 @@ def main():
         tests_total = sum_over_ranks(float(Jfr * len(pa)))
         # work actually done per test: tail terms summed by the kernel's rule
         # (cut at 2^-48 of the running sum, checked every 4 terms) on a sample of rows, 8 flop per
-        # term (4 DADD + 2 DMUL + 1 DFMA) + 300 flop of per-table setup; SURVEY.md 8d's model
+        # term (4 DADD + 2 DMUL + 1 DFMA) + 250 flop of per-table setup; SURVEY.md 8d's model
         # (32 flop per support point) is reported beside it
         sel = np.sort(np.random.default_rng(5).choice(Jfr, size=min(120, Jfr), replace=False))
         inc_h = inc[torch.from_numpy(sel).to(dev)].cpu().numpy().astype(np.float64)
         exc_h = exc[torch.from_numpy(sel).to(dev)].cpu().numpy().astype(np.float64)
         terms, support, trivial = fisher_work(inc_h[:, pa], inc_h[:, pb], exc_h[:, pa], exc_h[:, pb])
         fp64_peak = ops.probe_fp64(dev)
-        flops_per_test = 8.0 * terms + 300.0 * (1.0 - trivial)
+        flops_per_test = 8.0 * terms + 250.0 * (1.0 - trivial)
         tests_per_s = tests_total / (f_ms * 1e-3)
         useful = flops_per_test * tests_per_s / world / 1e12
         fisher = {"metric": "fisher_tests_per_s", "value": tests_per_s, "unit": "tests/s",
@@ -516,7 +516,7 @@ def main():
                              "mean_tail_terms_summed": terms},
                   "roofline": {"bound": "fp64", "achieved": useful, "peak": fp64_peak / 1e3, "unit": "TFLOP/s",
                                "frac": useful / (fp64_peak / 1e3), "flops_per_test": flops_per_test,
-                               "model": "8 flop per summed tail term + 300 flop per non-trivial table (per GPU); the FP64 "
+                               "model": "8 flop per summed tail term + 250 flop per non-trivial table (per GPU); the FP64 "
                                         "pipe issues DADD/DMUL at the DFMA rate and divergent lanes idle, so pipe "
                                         "occupancy (ncu) is the utilisation figure",
                                "pipe_fp64_active_ncu": fisher_pipe_active(),
