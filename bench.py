@@ -292,6 +292,12 @@ def main():
         run_reference(args, rank)
         return
 
+    # stdout carries exactly one JSON line: anything libraries print there meanwhile (NCCL announces
+    # its version on stdout at the first collective) goes to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     from splicedice_b200 import native, ops, sharding, synth
@@ -593,7 +599,8 @@ def main():
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps, "launch_mode": "cuda graph of K kernel launches" if graph is not None else "K stream launches",
             "clocks": clocks, "variants": variants, "fisher": fisher,
         }
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
