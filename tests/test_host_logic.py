@@ -290,3 +290,27 @@ def test_native_table_reader(tmp_path, golden_dir):
     empty.write_text("cluster\ts0\n")
     h, n, v = textio.read_table(str(empty))
     assert h == "cluster\ts0\n" and n == [] and v.shape[0] == 0
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the CPU arm the driver times next to the GPU arm): exactly one
+    line on stdout, valid JSON with the contract's keys; ranks other than 0 print nothing."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+           "--cpu-rows", "3000", "--samples", "16"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["metric"] == "quant_ps_cells_per_s" and line["unit"] == "cells/s"
+    assert line["value"] > 0 and line["higher_is_better"] is True and line["gpu_launches"] == 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    other = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root, env=env)
+    assert other.returncode == 0 and other.stdout.strip() == ""
