@@ -170,19 +170,28 @@ SD_HD double tail_fast(double p, double q, double u, double v)
     return t.A / t.Q;
 }
 
-// exp(x) for x <= ~1 (log-probabilities): k = rint(x / ln 2), r = x - k ln 2 in two FMA steps,
-// degree-13 Taylor polynomial on |r| <= 0.347 (truncation 4e-18), scaling by 2^k on the exponent
-// field.  ~2 ulp; x < -746 gives 0, results below 2^-1022 are rounded once by a final multiply.
-// The coefficients sit in constant memory so every DFMA takes its constant operand directly
-// (libdevice's exp spends two UMOV per coefficient on this target).
+// exp(x) for x <= ~1 (log-probabilities): n = rint(32 x / ln 2), r = x - n ln 2 / 32 in two FMA
+// steps (|r| <= ln 2 / 64 = 0.0108), exp(x) = 2^(n >> 5) * T[n & 31] * (1 + p(r)) with T[j] =
+// 2^(j/32) and p the degree-6 Taylor polynomial of expm1 (truncation r^7/5040 < 4e-18), scaling
+// by the power of two on the exponent field.  ~1 ulp, 12 FP64 operations (a degree-13 polynomial
+// on |r| <= 0.347 needed 19).  x < -746 gives 0, results below 2^-1022 are rounded once by a
+// final multiply.  On the device T sits in global memory behind the read-only cache (256 bytes,
+// per-lane index: the constant bank would serialise the lanes); the polynomial coefficients are
+// immediates / constant-bank operands of the DFMAs.
 #ifdef __CUDA_ARCH__
-#define SD_EXP_COEF __constant__
+#define SD_EXP_TAB __device__ const
 #else
-#define SD_EXP_COEF static const
+#define SD_EXP_TAB static const
 #endif
-SD_EXP_COEF double kExpCoef[12] = {
-    1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0,
-    1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5};
+SD_EXP_TAB double kExp2Tab[32] = {
+    1.0, 1.0218971486541166, 1.0442737824274138, 1.0671404006768237,
+    1.0905077326652577, 1.1143867425958924, 1.1387886347566916, 1.1637248587775775,
+    1.189207115002721, 1.215247359980469, 1.241857812073484, 1.2690509571917332,
+    1.2968395546510096, 1.3252366431597413, 1.3542555469368927, 1.383909881963832,
+    1.4142135623730951, 1.4451808069770467, 1.4768261459394993, 1.5091644275934228,
+    1.5422108254079407, 1.5759808451078865, 1.6104903319492543, 1.645755478153965,
+    1.681792830507429, 1.718619298122478, 1.7562521603732995, 1.7947090750031072,
+    1.8340080864093424, 1.8741676341103, 1.9152065613971474, 1.9571441241754002};
 
 SD_HD double add_exponent(double x, int k)      // x * 2^k, result normal
 {
@@ -197,18 +206,24 @@ SD_HD double exp_small(double x)
 {
     if (!(x >= -746.0)) return 0.0;
     const double kMagic = 6755399441055744.0;                  // 2^52 + 2^51: rint() in the low fraction bits
-    const double t = fma(x, 1.4426950408889634, kMagic);
-    const double kf = t - kMagic;
-    double r = fma(kf, -6.9314718055994529e-01, x);
-    r = fma(kf, -2.3190468138462996e-17, r);
-    double q = kExpCoef[0];
+    const double t = fma(x, 46.16624130844683, kMagic);        // 32 / ln 2
+    const double nf = t - kMagic;
+    double r = fma(nf, -0.02166084939249829, x);               // ln 2 / 32, hi and lo
+    r = fma(nf, -7.247021293269686e-19, r);
+    double p = fma(r, 1.0 / 720.0, 1.0 / 120.0);
+    p = fma(p, r, 1.0 / 24.0);
+    p = fma(p, r, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p *= r;                                                    // expm1(r)
+    const int n = (int)nf;
 #ifdef __CUDA_ARCH__
-#pragma unroll
+    const double tj = __ldg(&kExp2Tab[n & 31]);
+#else
+    const double tj = kExp2Tab[n & 31];
 #endif
-    for (int i = 1; i < 12; ++i) q = fma(q, r, kExpCoef[i]);
-    q = fma(q, r, 1.0);
-    q = fma(q, r, 1.0);
-    const int k = (int)kf;
+    const double q = fma(tj, p, tj);
+    const int k = n >> 5;                                      // floor(n / 32): arithmetic shift
     if (k >= -1020) return add_exponent(q, k);
     return add_exponent(q, k + 1000) * 9.3326361850321888e-302;   // 2^-1000
 }

@@ -38,3 +38,9 @@ extern "C" int fisher_twin_batch(int64_t count, const int64_t *a, const int64_t 
     for (int64_t i = 0; i < count; ++i) out[i] = (nmax < (int64_t(1) << 30) ? sd::fisher::two_sided<int32_t>(T, (int32_t)a[i], (int32_t)b[i], (int32_t)c[i], (int32_t)d[i]) : sd::fisher::two_sided<int64_t>(T, a[i], b[i], c[i], d[i]));
     return 0;
 }
+
+// exp_small on an array (tests/test_fisher_twin.py checks it against binary128 / mpmath)
+extern "C" void fisher_twin_exp(int64_t count, const double *x, double *out)
+{
+    for (int64_t i = 0; i < count; ++i) out[i] = sd::fisher::exp_small(x[i]);
+}

@@ -37,6 +37,14 @@ def twin():
         handle.fisher_twin_batch(ctypes.c_int64(len(t)), *[c.ctypes.data_as(i64p) for c in cols],
                                  out.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), ctypes.c_int64(cap))
         return out
+
+    def exp_small(x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        out = np.empty(len(x))
+        handle.fisher_twin_exp(ctypes.c_int64(len(x)), x.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                               out.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+        return out
+    run.exp_small = exp_small
     return run
 
 
@@ -83,3 +91,21 @@ def test_mirror_ties_are_included(twin):
     t = np.array(rows)
     want = fisher_c.fisher_two_sided(t[:, 0], t[:, 1], t[:, 2], t[:, 3])
     assert _max_rel(twin(t), want) < 1e-11
+
+
+def test_exp_small_against_long_double(twin):
+    """The kernel's own exp (table of 2^(j/32) + degree-6 polynomial) over the range of
+    log-probabilities: within 1.5 ulp of the exact value (numpy longdouble exp as the reference,
+    64-bit significand on x86-64), zero below -746, one final rounding in the subnormal range."""
+    rng = np.random.default_rng(7)
+    x = np.concatenate([-rng.random(400_000) * 700.0, -rng.random(200_000) * 5.0, rng.random(100_000) * 0.9,
+                        -10.0 ** rng.uniform(-12, 0, 100_000), np.array([0.0, -0.0, -1e-300, 0.5, -0.5, -708.0, -745.0])])
+    got = twin.exp_small(x)
+    want = np.exp(x.astype(np.longdouble))
+    rel = np.abs((got.astype(np.longdouble) - want) / want).astype(np.float64)
+    assert rel[x > -700.0].max() < 1.5 * 2.0 ** -52
+    low = x <= -700.0                                  # towards gradual underflow: one subnormal ulp at most
+    assert (np.abs(got[low].astype(np.longdouble) - want[low]) <= np.maximum(want[low] * 2.0 ** -51, 5e-324)).all()
+    assert (twin.exp_small(np.array([-746.5, -800.0, -1e308, -np.inf])) == 0.0).all()
+    sub = twin.exp_small(np.array([-720.0, -740.0, -745.0]))
+    assert (sub > 0).all() and np.allclose(sub, np.exp(np.array([-720.0, -740.0, -745.0])), rtol=1e-6, atol=5e-324)
