@@ -91,3 +91,26 @@ def test_one_giant_component():
     arrays = oracle_np.junctions_to_arrays(js)[:4]
     got, want = _compare(arrays)
     assert got["n_comp"] == 1 and got["nnz"] == 2 * 20000
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_dense_small_coordinates_and_three_strand_labels(seed):
+    """Junction sets drawn from a handful of coordinates (touching, nested, identical-start /
+    identical-end intervals and opposite-strand twins everywhere), chromosome names whose string
+    order differs from their numeric order and a third strand label ('.', which BED allows) --
+    the structure tests/test_reference_live.py pins against the reference with hypothesis."""
+    rng = np.random.default_rng(100 + seed)
+    chroms, strands = ["chr1", "chr11", "chr2", "MT", "1"], ["+", "-", "."]
+    n = int(rng.integers(1, 400))
+    out = set()
+    while len(out) < n:
+        a = int(rng.integers(0, 30))
+        out.add((chroms[int(rng.integers(0, 5))], a, a + int(rng.integers(1, 12)), strands[int(rng.integers(0, 3))]))
+    js = list(out)
+    rng.shuffle(js)
+    got, want = _compare(oracle_np.junctions_to_arrays(js)[:4])
+    # the oracle's adjacency is the brute-force closed-interval overlap on (chromosome, strand)
+    adj = oracle_np.adjacency_dict(js, want)
+    for j, lst in adj.items():
+        brute = {k for k in js if k != j and k[0] == j[0] and k[3] == j[3] and k[1] <= j[2] and j[1] <= k[2]}
+        assert set(lst) == brute and len(lst) == len(brute)

@@ -86,3 +86,31 @@ def test_fisher_oracle_against_scipy_live():
     got = fisher_c.fisher_two_sided(t[:, 0], t[:, 1], t[:, 2], t[:, 3])
     np.testing.assert_allclose(got, want, rtol=1e-9, atol=0)
     assert np.array_equal(got == 1.0, want == 1.0)
+
+
+def test_adjacency_property_on_dense_small_coordinates():
+    """hypothesis: junction sets drawn from a handful of coordinates (so touching, nested,
+    identical-start, identical-end and opposite-strand twins abound), chromosome names whose
+    string order differs from their numeric order, and a third strand label ('.', which BED
+    allows): the oracle's adjacency dict -- list order included -- and its component labels against
+    the reference's sweep; exclusion sums against a brute-force closed-interval overlap count."""
+    from hypothesis import given, settings, strategies as st
+
+    junction = st.tuples(st.sampled_from(["chr1", "chr11", "chr2", "MT", "1"]), st.integers(0, 12), st.integers(1, 9),
+                         st.sampled_from(["+", "-", "."])).map(lambda t: (t[0], t[1], t[1] + t[2], t[3]))
+
+    @settings(max_examples=120, deadline=None)
+    @given(st.sets(junction, min_size=1, max_size=40), st.randoms(use_true_random=False))
+    def check(jset, rnd):
+        js = list(jset)
+        rnd.shuffle(js)
+        clusters = ref_harness.ref_get_clusters(js)
+        csr = oracle_np.cluster_csr(*oracle_np.junctions_to_arrays(js)[:4])
+        assert oracle_np.adjacency_dict(js, csr) == clusters
+        assert ref_port.sweep_clusters(js) == clusters
+        # closed-interval overlap on the same chromosome and strand, brute force
+        for j, adj in clusters.items():
+            want = {k for k in js if k != j and k[0] == j[0] and k[3] == j[3] and k[1] <= j[2] and j[1] <= k[2]}
+            assert set(adj) == want and len(adj) == len(want)
+
+    check()
