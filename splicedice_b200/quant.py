@@ -183,6 +183,10 @@ class SPLICEDICE:
         print("Writing PS values...")
         self.writeAllpsi()
         print("\tDone", timer.check())
+        if getattr(self.args, "npz", False):
+            print("Writing PS matrix (npz)...")
+            self.writeNpz()
+            print("\tDone", timer.check())
         if self.args.drim:
             print("Writing drim table...")
             self.writeDrimTable()
@@ -360,6 +364,16 @@ class SPLICEDICE:
     def writeAllpsi(self):
         self._write_matrix(f"{self.outputPrefix}_allPS.tsv", np.ascontiguousarray(self.psi, dtype=np.float32))
 
+    def writeNpz(self):
+        """``{prefix}_allPS.npz`` with ``cols`` (sample names), ``rows`` (junction names) and
+        ``data`` (float32 PS, rows x cols) -- the layout findOutliers.py:117-118 loads and the
+        reference's README still names for the downstream commands; nothing in the reference
+        writes it, so this output is an addition behind ``--npz``."""
+        np.savez(f"{self.outputPrefix}_allPS.npz",
+                 cols=np.array([s.name for s in self.manifest]),
+                 rows=np.array([jn.junction_name(j) for j in self._rows]),
+                 data=np.ascontiguousarray(self.psi, dtype=np.float32))
+
     def writeDrimLine(self, i, junction, other, file):
         # the reference prints its float32 counts with astype(str): "34.0"
         values = "\t".join(f"{float(x)}" for x in self.counts[self.junctionIndex[other], :].tolist())
@@ -392,6 +406,8 @@ def add_parser(parser):
     parser.add_argument("--device", type=int, default=0, help="CUDA device ordinal")
     parser.add_argument("--threads", type=int, default=0, help="host threads for file parsing (0 = all)")
     parser.add_argument("--pythonIO", action="store_true", help="read the sample files with the plain python parser")
+    parser.add_argument("--npz", action="store_true",
+                        help="also write {prefix}_allPS.npz (cols / rows / data, the matrix layout findOutliers reads)")
 
 
 def run_with(args):

@@ -314,3 +314,29 @@ def test_bench_reference_arm_prints_one_json_line():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     other = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root, env=env)
     assert other.returncode == 0 and other.stdout.strip() == ""
+
+
+def test_npz_writer_layout(tmp_path):
+    """--npz: cols / rows / data exactly as findOutliers.py:117-118 unpacks them, data identical
+    to the matrix the TSV writer prints, NaN cells kept."""
+    import argparse
+    from splicedice_b200 import quant
+    p = argparse.ArgumentParser()
+    quant.add_parser(p)
+    man = tmp_path / "m.txt"
+    man.write_text("")
+    args = p.parse_args(["-m", str(man), "-o", str(tmp_path / "o"), "--npz"])
+    assert args.npz is True
+    job = quant.SPLICEDICE(args.manifest, args.output_prefix, args, run=False)
+
+    class S:
+        def __init__(self, name):
+            self.name = name
+    job.manifest = [S("a"), S("b"), S("c")]
+    job._rows = [("chr1", 5, 90, "+"), ("chr1", 7, 80, "-")]
+    job.psi = np.array([[0.25, np.nan, 1.0], [0.0, 0.5, 0.125]], dtype=np.float32)
+    job.writeNpz()
+    z = np.load(str(tmp_path / "o_allPS.npz"))
+    assert sorted(z.files) == ["cols", "data", "rows"]
+    assert z["cols"].tolist() == ["a", "b", "c"] and z["rows"].tolist() == ["chr1:5-90:+", "chr1:7-80:-"]
+    assert z["data"].dtype == np.float32 and np.array_equal(z["data"], job.psi, equal_nan=True)
