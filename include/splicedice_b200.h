@@ -122,15 +122,28 @@ int sd_quant_ps(int64_t n_junctions, int32_t n_samples,
                 int64_t row_begin, int64_t row_end,
                 uint32_t flags, void *stream);
 
+/* Name, template arguments, tile shape and grid of the kernel the calling thread's last
+ * sd_quant_ps / sd_ir_ratio call launched (diagnostics: bench.py reports it as roofline.kernel).
+ * Thread-local storage owned by the library; "" before the first launch. */
+const char *sd_quant_last_launch(void);
+
 /* Host-buffer form of the PS path (the call a ctypes user makes): counts / ps are HOST
  * pointers (pinned memory gives full PCIe rate), row_ptr / col_idx are HOST pointers.
- * Transfers and the kernel are pipelined over row blocks on internal streams; the call
- * returns when ps_f32 is complete.  `device` is the CUDA device ordinal. */
+ * Transfers and the kernel are pipelined over row blocks on streams the library keeps per
+ * device; row blocks whose counts are all below 65,536 cross the link as uint16 (narrowed by
+ * host threads into pinned staging, widened on the device) -- results do not depend on it.  The
+ * call returns when ps_f32 is complete; concurrent calls on one device are serialised.  Device
+ * buffers come from a pool private to the library and stay cached between calls
+ * (sd_host_pipeline_trim releases them).  `device` is the CUDA device ordinal.
+ * Environment (experiments): SD_QUANT_HOST_BLOCK_MB, SD_QUANT_HOST_U16=0, SD_HOST_THREADS. */
 int sd_quant_ps_host(int device, int64_t n_junctions, int32_t n_samples,
                      const int32_t *counts, int64_t ld_counts,
                      const int32_t *row_ptr, const int32_t *col_idx,
                      const uint8_t *low_mask, int64_t ld_mask,
                      float *ps_f32, int64_t ld_ps32);
+
+/* Releases the device memory and pinned staging the host-buffer calls keep cached for `device`. */
+int sd_host_pipeline_trim(int device);
 
 /* ---- K3: pairwise two-sided Fisher exact test ------------------------------------
  * Replaces the hot loop of pairwise_fisher.run_with (pairwise_fisher.py:154-180) and

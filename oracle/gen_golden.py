@@ -132,6 +132,96 @@ def gen_cli_case(name, junctions, counts, quant_over=None, pairwise=True):
         json.dump(quant_over, f)
 
 
+# --- every sample-file type on every filter boundary (SPLICEDICE.py:162-228, 257-295) -----------
+MIXED_VARIANTS = {
+    "default": {},
+    "strict": dict(noMultimap=True, minOverhang=8, minEntropy=1.5, lowCoverageNan=True, minUnique=7),
+    "lengths": dict(maxLength=1000, minLength=100, lowCoverageNan=True),
+}
+
+
+def write_mixed_inputs(dirname, seed=31):
+    """A manifest of SJ.out.tab, tagged ``splicedicebed``, plain BED and leafcutter files (plus a
+    ``.bam`` and an unknown suffix, which quant opens and ignores) drawn from a small coordinate
+    pool so that the same junction recurs across files with scores either side of minUnique, with
+    lengths on both sides of every length bound of MIXED_VARIANTS (strict for SJ, inclusive for
+    BED), every SJ strand / motif code, overhang / entropy tags on their thresholds, annotated
+    and unannotated tags, '.' strands and repeated lines (the last one wins)."""
+    os.makedirs(dirname, exist_ok=True)
+    rng = np.random.default_rng(seed)
+    spans = [49, 50, 51, 99, 100, 101, 999, 1000, 1001, 49999, 50000, 50001, 300, 700, 4000]
+    chroms = ["chr1", "chr10", "chr2"]
+    starts = [1000, 1040, 1300, 2000, 2050, 60000]
+
+    def draw():
+        c = chroms[int(rng.integers(0, 3))]
+        left = starts[int(rng.integers(0, len(starts)))]
+        return c, left, left + spans[int(rng.integers(0, len(spans)))]
+
+    def sj_lines(n):
+        out = []
+        for _ in range(n):
+            c, left, right = draw()
+            strand = int(rng.choice([0, 1, 1, 2, 2]))
+            motif = int(rng.choice([0, 1, 1, 2, 2, 3, 4, 5, 6]))
+            uniq, multi = int(rng.integers(0, 10)), int(rng.integers(0, 6))
+            out.append(f"{c}\t{left + 1}\t{right}\t{strand}\t{motif}\t{int(rng.integers(0, 2))}\t{uniq}\t{multi}\t"
+                       f"{int(rng.integers(1, 40))}\n")
+        return out
+
+    def tagged_lines(n):
+        out = []
+        for _ in range(n):
+            c, left, right = draw()
+            e1, e2 = (float(rng.choice([0.5, 0.99, 1.0, 1.01, 1.49, 1.5, 1.51, 2.2])) for _ in range(2))
+            over = int(rng.choice([3, 4, 5, 6, 7, 8, 9, 20]))
+            annot = str(rng.choice(["?", "?", "?", "GENE1", "ENSG0001"]))
+            strand = str(rng.choice(["+", "+", "-", "-", "."]))
+            out.append(f"{c}\t{left}\t{right}\te:{e1:0.02f}:{e2:0.02f};o:{over};m:GT_AG;a:{annot}\t"
+                       f"{int(rng.integers(0, 14))}\t{strand}\n")
+        return out
+
+    def plain_lines(n, tag):
+        out = []
+        for k in range(n):
+            c, left, right = draw()
+            strand = str(rng.choice(["+", "+", "-", "-", "."]))
+            out.append(f"{c}\t{left}\t{right}\t{tag}{k}\t{int(rng.integers(0, 14))}\t{strand}\n")
+        return out
+
+    files = {
+        "a.SJ.out.tab": sj_lines(260), "b.SJ.out.tab": sj_lines(260),
+        "c.bed": tagged_lines(260), "d.bed": tagged_lines(260),
+        "e.junc.bed": plain_lines(220, "j"), "f.leafcutter.junc": plain_lines(220, "lc"),
+        "g.bam": ["not a junction file\n"], "h.txt": plain_lines(20, "u"),
+    }
+    # repeated lines: the later score replaces the earlier one (SPLICEDICE.py:274)
+    for name in ("a.SJ.out.tab", "c.bed", "e.junc.bed"):
+        files[name] += files[name][:25][::-1]
+    man = []
+    for k, (name, lines) in enumerate(files.items()):
+        path = os.path.join(dirname, name)
+        with open(path, "w") as f:
+            f.writelines(lines)
+        man.append(f"s{k}_{name.split('.')[0]}\t{path}\tmeta{k}\tcond{k % 2}\n")
+    mpath = os.path.join(dirname, "manifest.txt")
+    with open(mpath, "w") as f:
+        f.writelines(man)
+    return mpath
+
+
+def gen_mixed_case():
+    d = case_dir("mixed_formats")
+    manifest = write_mixed_inputs(os.path.join(d, "input"))
+    for tag, over in MIXED_VARIANTS.items():
+        exp = os.path.join(d, f"expected_{tag}")
+        os.makedirs(exp)
+        run_reference_quant(manifest, os.path.join(exp, "ref"), **over)
+    relpath_manifest(manifest, d)
+    with open(os.path.join(d, "variants.json"), "w") as f:
+        json.dump(MIXED_VARIANTS, f, indent=1)
+
+
 def gen_inmemory_quant(name, junctions, n_samples, seed, zero_frac=0.3, n_low=60):
     """getClusters + calculatePsi on injected data; adjacency stored as row lists."""
     rng = np.random.default_rng(seed)
@@ -270,6 +360,9 @@ def main():
     # a 5-sample slice for pairwise (10 pairs x ~80 events)
     js5 = js[:80]
     gen_cli_case("cli_5x_pairwise", js5, counts[:80, :5])
+
+    # 2b. all four sample-file types x three flag sets
+    gen_mixed_case()
 
     # 3. in-memory getClusters + calculatePsi
     gen_inmemory_quant("quant_adversarial", synth.adversarial_tuples(1), 6, seed=21)

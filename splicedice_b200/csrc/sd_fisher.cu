@@ -24,8 +24,8 @@
 namespace sd {
 
 // kMode 0: every index is inside the staged shared-memory prefix; 1: shared prefix + global
-// table; 2: as 1, plus lgamma() beyond the table cap.
-__device__ __noinline__ double lgfact_fallback(double k) { return lgamma(k + 1.0); }
+// table; 2: as 1, plus the double-double Stirling series (fisher::lgfact_stirling) beyond the
+// table cap.
 
 template <int kMode>
 struct DeviceTable {
@@ -50,7 +50,14 @@ struct DeviceTable {
         if (kMode == 0) return lds2(smem + (uint32_t)k * 16u);
         if ((int64_t)k < n_smem) return lds2(smem + (uint32_t)k * 16u);
         if (kMode == 1 || (int64_t)k < n_gmem) return __ldg(gmem + k);
-        return make_double2(lgfact_fallback((double)k), 0.0);
+        const fisher::dd v = fisher::lgfact_stirling(*this, (double)k);
+        return make_double2(v.hi, v.lo);
+    }
+    // entries the table is guaranteed to hold (k < 4096 <= n_gmem): no fallback branch
+    __device__ __forceinline__ fisher::dd in_table(int32_t k) const
+    {
+        const double2 v = (int64_t)k < n_smem ? lds2(smem + (uint32_t)k * 16u) : __ldg(gmem + k);
+        return fisher::dd_make(v.x, v.y);
     }
     template <class Int>
     __device__ __forceinline__ double hi(Int k) const
@@ -357,7 +364,7 @@ __global__ void __launch_bounds__(256) fisher_scan_tables(int64_t n, const int64
 
 // ---- device copies of the table: one per device, grown on demand, never shrunk ----------
 namespace {
-constexpr int64_t kTableCap = int64_t(1) << 22;      // 4 Mi entries = 64 MB; beyond: lgamma()
+constexpr int64_t kTableCap = int64_t(1) << 22;      // 4 Mi entries = 64 MB; beyond: fisher::lgfact_stirling
 constexpr int kMaxDevices = 64;
 std::mutex g_tab_mu;
 double2 *g_tab_dev[kMaxDevices] = {};

@@ -235,6 +235,64 @@ SD_HD dd acc_result(double sum, double err)
     return dd_make(hi, err - (hi - sum));
 }
 
+// log k! for k beyond the log-factorial table, in double-double: Stirling's series
+//   log k! = (k + 1/2) log k - k + log(2 pi)/2 + 1/(12 k) - 1/(360 k^3) + ...
+// (k >= 4096 here: the k^-3 term is below 7e-14 and kept, the k^-5 term below 7e-22 is dropped;
+// the table itself covers 2^22 entries, where both vanish).  A binary64 lgamma() is not enough: at
+// k = 4e6, log k! = 5.7e7 carries 7e-9 of rounding error, more than the 1e-9 relative the p-values
+// are promised to.  log k comes from the table itself: k = 2^s (c + delta) with c an integer in
+// [1024, 2048] and |delta| <= 1/2, so
+//   log k = s ln 2 + (lg[c] - lg[c-1]) + log1p(delta / c),    |delta / c| <= 2^-11,
+// the quotient and its square carried in double-double, the series to the eighth power.  The
+// result is good to ~1e-14 absolute at k = 2^33 (1e-17 at 2^23); checked against binary128
+// lgammaq in tests/test_fisher_twin.py.  Out of line: this is the rare path.
+template <class Table>
+SD_NOINLINE dd lgfact_stirling(Table tab, double k)
+{
+    int e;
+    const double m = frexp(k, &e) * 2048.0;                  // [1024, 2048), exact
+    const double c = rint(m);
+    const double delta = m - c;                              // exact (Sterbenz)
+    const int s = e - 11;
+    // r = delta / c in double-double
+    const double r_hi = delta / c;
+    const double r_lo = fma(-r_hi, c, delta) / c;
+    // log1p(r) = r - r^2/2 + r^3/3 - ... - r^8/8
+    const double sq_hi = r_hi * r_hi;
+    const double sq_lo = fma(r_hi, r_hi, -sq_hi) + 2.0 * r_hi * r_lo;
+    double t = fma(r_hi, -1.0 / 8.0, 1.0 / 7.0);
+    t = fma(t, r_hi, -1.0 / 6.0);
+    t = fma(t, r_hi, 1.0 / 5.0);
+    t = fma(t, r_hi, -1.0 / 4.0);
+    t = fma(t, r_hi, 1.0 / 3.0);
+    t *= sq_hi * r_hi;                                       // r^3/3 - ... : below 4e-11, plain double
+    double sum = r_hi, err = r_lo + t;
+    acc_two_sum(sum, err, -0.5 * sq_hi, -0.5 * sq_lo);
+    // + log c = lg[c] - lg[c-1]
+    const dd lc = tab.in_table((int32_t)c), lc1 = tab.in_table((int32_t)c - 1);   // every table holds >= 4096 entries
+    acc_two_sum(sum, err, lc.hi, lc.lo);
+    acc_two_sum(sum, err, -lc1.hi, -lc1.lo);
+    // + s ln 2 (s < 64: the product with the hi word is exact to 6 spare bits only if split --
+    // use an FMA pair instead)
+    {
+        const double sd = (double)s;
+        const double p_hi = sd * 0.6931471805599453;
+        const double p_lo = fma(sd, 0.6931471805599453, -p_hi) + sd * 2.3190468138462996e-17;
+        acc_two_sum(sum, err, p_hi, p_lo);
+    }
+    const dd logk = acc_result(sum, err);
+    // (k + 1/2) * log k: k + 1/2 is exact below 2^52
+    const double kh = k + 0.5;
+    const double q_hi = kh * logk.hi;
+    const double q_lo = fma(kh, logk.hi, -q_hi) + kh * logk.lo;
+    sum = q_hi; err = q_lo;
+    acc_two_sum(sum, err, -k, 0.0);
+    acc_two_sum(sum, err, 0.9189385332046728, -3.8782941580672414e-17);
+    const double ik = 1.0 / k;
+    acc_two_sum(sum, err, ik * (1.0 / 12.0), -ik * ik * ik * (1.0 / 360.0));
+    return acc_result(sum, err);
+}
+
 // Per-sample terms of a table column (inc, exc): both depend on one sample only, so the pairwise
 // kernel computes them once per (junction, sample) instead of once per pair.  Kept as unnormalised
 // (sum, err) pairs of a compensated sum -- TwoSum on the hi words, rounding errors and lo words

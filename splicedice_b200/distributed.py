@@ -53,10 +53,33 @@ def _world():
     return 0, 1
 
 
+def all_gather_rows(local, parts):
+    """Row slabs -> the whole [J, ...] tensor on every rank.  ``local`` holds this rank's rows
+    ``parts[rank]``; slab heights differ (cuts sit on cluster boundaries).  NCCL: one
+    ``dist.all_gather`` whose outputs are the slab views of the result itself -- torch issues it as
+    one grouped NCCL call that lands every slab in place, no padding and no second copy.  Other
+    backends (gloo in the CPU tests) need equal blocks: slabs are padded to a common height."""
+    rank, world = _world()
+    if world == 1:
+        return local
+    J = parts[-1][1]
+    if dist.get_backend() == "nccl" and local.is_cuda:
+        full = torch.empty((J,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.all_gather([full[a:b] for a, b in parts], local.contiguous())
+        return full
+    r0, r1 = parts[rank]
+    height = max(b - a for a, b in parts)
+    padded = torch.zeros((height,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    padded[: r1 - r0] = local
+    blocks = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(blocks, padded)
+    return torch.cat([blocks[k][: parts[k][1] - parts[k][0]] for k in range(world)])
+
+
 def sharded_rows(counts, row_ptr, col_idx, slab_fn, gather=True, weights=None):
     """Run ``slab_fn(counts[r0:r1], local_row_ptr, local_col_idx) -> tensor[r1 - r0, S]`` on this
-    rank's slab.  With ``gather`` every rank receives the full [J, S] tensor (slabs padded to a
-    common height for the all-gather); otherwise returns (local tensor, (r0, r1))."""
+    rank's slab.  With ``gather`` every rank receives the full [J, S] tensor (all_gather_rows);
+    otherwise returns (local tensor, (r0, r1))."""
     rank, world = _world()
     n_samples = counts.shape[1]
     if weights is None:
@@ -67,14 +90,7 @@ def sharded_rows(counts, row_ptr, col_idx, slab_fn, gather=True, weights=None):
     local = slab_fn(counts[r0:r1], rp, ci)
     if not gather:
         return local, (r0, r1)
-    if world == 1:
-        return local
-    height = max(b - a for a, b in parts)
-    padded = torch.zeros((height,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    padded[: r1 - r0] = local
-    blocks = [torch.empty_like(padded) for _ in range(world)]
-    dist.all_gather(blocks, padded)
-    return torch.cat([blocks[k][: parts[k][1] - parts[k][0]] for k in range(world)])
+    return all_gather_rows(local, parts)
 
 
 def quant_ps_sharded(counts_host, row_ptr, col_idx, device=None, gather=True, low_mask=None):

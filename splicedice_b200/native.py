@@ -49,7 +49,9 @@ _SIGNATURES = {
     "sd_cluster_fill": (c_int, [c_int64, c_int64, _P, _P, _P, _P, c_size_t, _P, c_size_t, _P]),
     "sd_quant_ps": (c_int, [c_int64, c_int32, _P, c_int64, _P, _P, _P, c_int64, _P, c_int64,
                             _P, c_int64, _P, c_int64, c_int64, c_int64, c_uint32, _P]),
+    "sd_quant_last_launch": (c_char_p, []),
     "sd_quant_ps_host": (c_int, [c_int, c_int64, c_int32, _P, c_int64, _P, _P, _P, c_int64, _P, c_int64]),
+    "sd_host_pipeline_trim": (c_int, [c_int]),
     "sd_fisher_pairwise": (c_int, [c_int64, c_int32, _P, c_int64, _P, c_int64, c_int64, _P, _P,
                                    _P, c_int64, c_int64, c_int64, _P]),
     "sd_fisher_pairwise_bounded": (c_int, [c_int64, c_int32, _P, c_int64, _P, c_int64, c_int64, _P, _P,

@@ -118,6 +118,23 @@ class _NativeIngest:
         return counts, mask
 
 
+class LowCells:
+    """The reference's ``low`` list of (row, sample) cells (SPLICEDICE.py:275-276) held as the
+    native reader's uint8 mask; the tuples are only materialised if somebody iterates."""
+
+    def __init__(self, mask):
+        self.mask = mask
+
+    def __len__(self):
+        return int(np.count_nonzero(self.mask))
+
+    def __bool__(self):
+        return bool(self.mask.any())
+
+    def __iter__(self):
+        return (tuple(x) for x in np.argwhere(self.mask).tolist())
+
+
 class Timer:
     """Stage timer printing the reference's ``[h:mm:ss.ss]`` stamps (SPLICEDICE.py:48-66)."""
 
@@ -290,8 +307,7 @@ class SPLICEDICE:
             return self._getJunctionCounts_py()
         ing = getattr(self, "_ingest", None) or _NativeIngest(self.manifest, self.args)
         counts, mask = ing.counts(self._rows)
-        low = [tuple(x) for x in np.argwhere(mask).tolist()] if mask is not None else []
-        return counts, low
+        return counts, (LowCells(mask) if mask is not None else [])
 
     def _getJunctionCounts_py(self):
         index = self.junctionIndex
@@ -325,7 +341,9 @@ class SPLICEDICE:
         --lowCoverageNan, on the low cells (SPLICEDICE.py:297-310)."""
         from . import ops
         mask = None
-        if self.args.lowCoverageNan and self.low:
+        if self.args.lowCoverageNan and isinstance(self.low, LowCells):
+            mask = self.low.mask if self.low else None
+        elif self.args.lowCoverageNan and self.low:
             mask = np.zeros(self.counts.shape, dtype=np.uint8)
             rows, cols = zip(*self.low)
             mask[list(rows), list(cols)] = 1

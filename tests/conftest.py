@@ -12,11 +12,12 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
-    config.addinivalue_line("markers", "needs_reference: needs /root/reference (build container only)")
+    config.addinivalue_line("markers", "needs_reference: needs the reference tree (/root/reference, or its install under oracle/_ref)")
 
 
 def pytest_collection_modifyitems(config, items):
-    have_ref = os.path.isfile("/root/reference/splicedice/SPLICEDICE.py")
+    have_ref = (os.path.isfile("/root/reference/splicedice/SPLICEDICE.py")
+                or os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "splicedice", "SPLICEDICE.py")))
     skip_ref = pytest.mark.skip(reason="reference tree not present on this machine")
     for item in items:
         if "needs_reference" in item.keywords and not have_ref:

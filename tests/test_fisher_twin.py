@@ -44,7 +44,14 @@ def twin():
         handle.fisher_twin_exp(ctypes.c_int64(len(x)), x.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
                                out.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
         return out
+    def stirling(k):
+        k = np.ascontiguousarray(k, dtype=np.int64)
+        outs = [np.empty(len(k)) for _ in range(4)]
+        dp = ctypes.POINTER(ctypes.c_double)
+        handle.fisher_twin_stirling(ctypes.c_int64(len(k)), k.ctypes.data_as(i64p), *[o.ctypes.data_as(dp) for o in outs])
+        return outs
     run.exp_small = exp_small
+    run.stirling = stirling
     return run
 
 
@@ -74,11 +81,48 @@ def test_random_vs_binary128(twin, scale, n):
     assert _max_rel(twin(t), want) < 1e-11
 
 
-def test_beyond_the_table_cap_uses_lgamma(twin):
+def test_log_factorial_beyond_the_table_is_double_double(twin):
+    """fisher::lgfact_stirling (what the kernel uses for k >= 2^22, the table cap) against binary128
+    lgammaq: the hi word is the correctly rounded double and hi + lo is within 2e-14 absolute up to
+    2^33 (3e-16 relative to nothing: log k! is ~1e11 there) -- a plain lgamma() is 7e-9 off at 4e6,
+    more than the 1e-9 the p-values are promised to."""
+    rng = np.random.default_rng(1)
+    k = np.unique(np.concatenate([
+        np.arange(4096, 4200), 2 ** np.arange(12, 34), 2 ** np.arange(12, 34) - 1, 2 ** np.arange(12, 34) + 1,
+        rng.integers(4096, 1 << 22, 3000), rng.integers(1 << 22, 1 << 26, 3000), rng.integers(1 << 26, 1 << 33, 3000)]))
+    hi, lo, want_hi, want_lo = twin.stirling(k)
+    err = np.abs((hi - want_hi) + (lo - want_lo))
+    assert (hi == want_hi).all()
+    assert err[k < (1 << 26)].max() < 2e-16 and err.max() < 2e-14
+    plain = np.abs(np.array([float(__import__("math").lgamma(x + 1.0)) for x in k[-200:]]) - want_hi[-200:])
+    assert plain.max() > 1e-7                                   # what the double-double form is for
+
+
+def test_beyond_the_table_cap(twin):
+    """Totals above the table (cap forced to 4,096 entries, totals up to 60,000): the Stirling
+    fallback keeps the full tolerance, exact mirror ties included."""
     rng = np.random.default_rng(3)
-    t = rng.integers(0, 3000, size=(5000, 4))
+    t = rng.integers(0, 15000, size=(3000, 4))
+    t[::5] = np.stack([t[::5, 0], t[::5, 1], t[::5, 1], t[::5, 0]], axis=1)       # mirror ties
     want = fisher_c.fisher_two_sided(t[:, 0], t[:, 1], t[:, 2], t[:, 3])
-    assert _max_rel(twin(t, cap=900), want) < 1e-9
+    assert _max_rel(twin(t, cap=4096), want) < 1e-11
+
+
+def test_totals_straddling_the_real_table_cap(twin):
+    """Cells of 1-3 million (totals either side of 2^22 = 4,194,304) against the binary128 oracle."""
+    rng = np.random.default_rng(12)
+    rows = []
+    for total in (3_900_000, 4_194_303, 4_194_304, 4_194_305, 4_500_000, 6_000_000):
+        for skew in (0.0, 0.001, 0.004):
+            n1 = int(total * rng.uniform(0.3, 0.7)); n = int(total * rng.uniform(0.3, 0.7))
+            a = int(n1 * n / total * (1.0 + skew))
+            rows.append([a, n1 - a, n - a, total - n1 - n + a])
+    t = np.array(rows)
+    assert (t >= 0).all()
+    want = fisher_c.fisher_two_sided(t[:, 0], t[:, 1], t[:, 2], t[:, 3])
+    assert (want < 1.0).any() and (want > 1e-300).sum() >= 10
+    assert _max_rel(twin(t), want) < 1e-9                      # twin table covers these totals entirely
+    assert _max_rel(twin(t, cap=1 << 22), want) < 1e-9         # the kernel's situation: table capped at 2^22
 
 
 def test_mirror_ties_are_included(twin):

@@ -63,6 +63,24 @@ def test_quant_files_are_byte_identical(case, golden_dir, tmp_path, capsys):
     _same(str(tmp_path / "r_allClusters.tsv"), os.path.join(exp, "c2ps_r_allClusters.tsv"))
 
 
+@pytest.mark.parametrize("native_io", [True, False], ids=["native", "python"])
+@pytest.mark.parametrize("variant", ["default", "strict", "lengths"])
+def test_quant_mixed_sample_formats_byte_identical(variant, native_io, golden_dir, tmp_path):
+    """SJ.out.tab + tagged BED + plain BED + leafcutter (+ .bam / unknown suffix) in one manifest,
+    every filter on its boundary, three flag sets: the four files the reference wrote
+    (SPLICEDICE.py:162-228 junction union, :257-295 counts and low cells, :297-310 PS)."""
+    from splicedice_b200 import quant
+    from tests.test_ingest_golden import absolute_manifest, variant_argv
+    case_dir = os.path.join(golden_dir, "mixed_formats")
+    over = json.load(open(os.path.join(case_dir, "variants.json")))[variant]
+    argv = ["-m", absolute_manifest(case_dir, tmp_path), "-o", str(tmp_path / "out")] + variant_argv(over)
+    if not native_io:
+        argv.append("--pythonIO")
+    quant.run_with(_args(quant, argv))
+    for suffix in ("_allClusters.tsv", "_junctions.bed", "_inclusionCounts.tsv", "_allPS.tsv"):
+        _same(str(tmp_path / f"out{suffix}"), os.path.join(case_dir, f"expected_{variant}", f"ref{suffix}"))
+
+
 def test_quant_api_shapes_match_the_reference(golden_dir, tmp_path):
     """getClusters() -> dict of tuples with the reference's list order; calculatePsi() -> float32."""
     from splicedice_b200 import quant

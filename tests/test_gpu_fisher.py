@@ -130,7 +130,7 @@ def test_bounded_entry_point_matches_and_guards():
 
 def test_kernel_instantiations_agree():
     """Every instantiation of the pairwise kernel on the same tables: staged table (mode 0), table
-    partly / wholly in global memory (modes 1, 2 with the lgamma fallback, chosen through the
+    partly / wholly in global memory (modes 1, 2 with the Stirling fallback, chosen through the
     promised bound), 64-bit totals (the pair-order kernel), the plain kernel by environment
     switch -- and more than 512 samples, where the junction row is not staged in shared memory."""
     import os
@@ -182,3 +182,31 @@ def test_kernel_instantiations_agree():
     got2 = ops.fisher_pairwise(torch.from_numpy(counts2).to(dev), torch.from_numpy(exc2).to(dev), qa, qb).cpu().numpy()
     want2 = fisher_c.pairwise(counts2, exc2, qa, qb)
     _check(got2.ravel(), want2.ravel(), rtol=1e-11)
+
+
+def test_totals_straddling_the_table_cap():
+    """Table totals either side of 2^22 (the log-factorial table's cap): beyond it the kernel uses
+    the double-double Stirling series (fisher::lgfact_stirling), which keeps the 1e-9 contract where
+    a binary64 lgamma() (7e-9 of rounding at log 4e6!) would not.  Element-wise kernel and the
+    pairwise kernels (cells of 1-3 million), against the binary128 oracle."""
+    _, ops = _ops()
+    rng = np.random.default_rng(12)
+    rows = []
+    for total in (3_900_000, 4_194_303, 4_194_304, 4_194_305, 4_500_000, 6_000_000, 8_000_000):
+        for skew in (0.0, 0.001, 0.004):
+            n1 = int(total * rng.uniform(0.3, 0.7)); n = int(total * rng.uniform(0.3, 0.7))
+            a = int(n1 * n / total * (1.0 + skew))
+            rows.append([a, n1 - a, n - a, total - n1 - n + a])
+    t = np.array(rows)
+    want = fisher_c.fisher_two_sided(t[:, 0], t[:, 1], t[:, 2], t[:, 3])
+    got = ops.fisher_tables(t[:, 0], t[:, 1], t[:, 2], t[:, 3]).cpu().numpy()
+    _check(got, want)
+    # pairwise form: 4 samples whose (inc, exc) columns are the table columns above
+    dev = torch.device("cuda", 0)
+    inc = np.stack([t[:, 0], t[:, 1], t[:, 1], t[:, 0]], axis=1).astype(np.int32)
+    exc = np.stack([t[:, 2], t[:, 3], t[:, 3] // 2, t[:, 2] + 7], axis=1).astype(np.int64)
+    pa, pb = oracle_np.all_pairs(4)
+    wantp = fisher_c.pairwise(inc, exc, pa, pb)
+    gotp = ops.fisher_pairwise(torch.from_numpy(inc).to(dev), torch.from_numpy(exc).to(dev), pa, pb).cpu().numpy()
+    _check(gotp.ravel(), wantp.ravel())
+    np.testing.assert_array_equal(gotp[:, 0], got)

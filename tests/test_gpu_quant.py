@@ -117,6 +117,36 @@ def test_host_pipeline_matches_device_path():
     np.testing.assert_array_equal(util.bits32(out), util.bits32(want))
 
 
+@pytest.mark.parametrize("u16", ["1", "0"])
+def test_host_pipeline_blocks_ring_and_wide_values(u16, monkeypatch):
+    """sd_quant_ps_host over many small row blocks (the pinned staging ring wraps several times),
+    with the uint16 link format on and off, on a matrix where some blocks hold counts of 65,536
+    and above or exactly 65,535 (those blocks must cross as int32 / still fit), an unaligned
+    sample count and a strided host matrix: PS bits equal the oracle's in every case, twice in a
+    row (the per-device context and its pool are reused), and after a trim."""
+    native, ops = _ops()
+    J, S = 30000, 301
+    _, csr, counts = util.synthetic_problem(J, S, seed=13)
+    counts = counts.astype(np.int32)
+    counts[5000:5003, 7] = [65535, 65536, 1 << 20]
+    counts[17000, :] = 70000
+    counts[29999, 300] = 65535
+    want = oracle_np.ps_f32(counts, csr["row_ptr"], csr["col_idx"])
+    monkeypatch.setenv("SD_QUANT_HOST_BLOCK_MB", "1")
+    monkeypatch.setenv("SD_QUANT_HOST_U16", u16)
+    pinned = torch.from_numpy(counts).pin_memory()
+    for _ in range(2):
+        out = ops.quant_ps_host(pinned, csr["row_ptr"], csr["col_idx"]).numpy()
+        np.testing.assert_array_equal(util.bits32(out), util.bits32(want))
+    native.call("sd_host_pipeline_trim", 0)
+    wide = np.zeros((J, S + 11), dtype=np.int32)                 # ld_counts > n_samples, pageable memory
+    wide[:, :S] = counts
+    out = ops.quant_ps_host(torch.from_numpy(wide)[:, :S], csr["row_ptr"], csr["col_idx"]).numpy()
+    np.testing.assert_array_equal(util.bits32(out), util.bits32(want))
+    tiny = ops.quant_ps_host(counts[:3].copy(), np.zeros(4, dtype=np.int32), np.zeros(0, dtype=np.int32)).numpy()
+    assert np.isnan(tiny[counts[:3] == 0]).all() and (tiny[counts[:3] > 0] == 1.0).all()
+
+
 def test_device_synth_matches_host_generator():
     native, ops = _ops()
     from splicedice_b200 import synth

@@ -294,14 +294,16 @@ def test_native_table_reader(tmp_path, golden_dir):
 
 def test_bench_reference_arm_prints_one_json_line():
     """`bench.py --impl reference` (the CPU arm the driver times next to the GPU arm): exactly one
-    line on stdout, valid JSON with the contract's keys; ranks other than 0 print nothing."""
+    line on stdout, valid JSON with the contract's keys, the same `config` the GPU arm prints; ranks
+    other than 0 print nothing.  The timed code is the unmodified reference when oracle/_ref (or
+    /root/reference) is present, the port otherwise -- the line says which."""
     import json
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-           "--cpu-rows", "3000", "--samples", "16"]
+           "--junctions", "3000", "--samples", "16", "--cpu-workers", "2"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
@@ -309,11 +311,41 @@ def test_bench_reference_arm_prints_one_json_line():
     line = json.loads(lines[0])
     assert line["impl"] == "reference" and line["metric"] == "quant_ps_cells_per_s" and line["unit"] == "cells/s"
     assert line["value"] > 0 and line["higher_is_better"] is True and line["gpu_launches"] == 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    from oracle import ref_harness
+    assert line["cpu_baseline"]["kind"] == ("reference" if ref_harness.available() else "port")
+    assert line["cpu_baseline"]["cores"] == 2 and line["cpu_baseline"]["value"] == line["value"]
     assert line["e2e"] == {"value": line["value"], "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    import argparse
+    import bench
+    assert line["config"] == bench.base_config(argparse.Namespace(samples=16, junctions=3000))
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     other = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root, env=env)
     assert other.returncode == 0 and other.stdout.strip() == ""
+
+
+def test_reference_fan_out_equals_one_process():
+    """oracle/ref_harness.ref_quant_seconds: the closed-row-slab fan-out of the reference's own
+    getClusters / calculatePsi gives the same PS matrix (checksum, NaN count) as one process on the
+    whole problem, and the slabs are closed under overlap."""
+    from oracle import ref_harness
+    if not ref_harness.available():
+        pytest.skip("no reference tree (neither /root/reference nor oracle/_ref)")
+    from splicedice_b200 import synth
+    rows = sorted(set(synth.junction_tuples(5000, 3)) | set(synth.adversarial_tuples(4)))
+    counts = synth.counts_host(7, 0, len(rows), 12).astype(np.float32)
+    counts[::7] = 0
+    keep = np.zeros(counts.shape, dtype=np.float32)
+    with ref_harness.warnings_off():
+        _, sum1, nan1 = ref_harness.ref_quant_seconds(rows, counts, 1, keep=keep)
+        _, sum3, nan3 = ref_harness.ref_quant_seconds(rows, counts, 3)
+    assert nan1 == nan3 and nan1 == int(np.isnan(keep).sum()) and abs(sum1 - sum3) <= 1e-9 * abs(sum1)
+    slabs = ref_harness.closed_row_slabs(rows, 18)
+    assert slabs[0][0] == 0 and slabs[-1][1] == len(rows) and all(a[1] == b[0] for a, b in zip(slabs, slabs[1:]))
+    clusters = ref_harness.ref_get_clusters(rows)
+    index = {j: i for i, j in enumerate(rows)}
+    for a, b in slabs:
+        for j in rows[a:b]:
+            assert all(a <= index[o] < b for o in clusters[j])
 
 
 def test_npz_writer_layout(tmp_path):
