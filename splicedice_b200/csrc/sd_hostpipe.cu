@@ -14,7 +14,10 @@
 //     full-duplex link that is already at its combined ceiling the D2H direction then runs at its
 //     own rate.  The decision is per block (one value >= 65,536 or < 0 sends that block as int32),
 //     so results never depend on it.
+#include <immintrin.h>
 #include <sched.h>
+
+#include <chrono>
 
 #include <algorithm>
 #include <atomic>
@@ -58,7 +61,12 @@ private:
             cpu_set_t set;
             int cpus = (int)std::thread::hardware_concurrency();
             if (sched_getaffinity(0, sizeof set, &set) == 0) cpus = CPU_COUNT(&set);
-            n = std::min(8, std::max(1, cpus / 2));
+            // half of the CPUs this process may use, shared between the ranks of one torchrun job; more
+            // than 8 threads only adds host-memory traffic that slows the D2H stream (measured on a
+            // 16-vCPU B200 box, 400,000 x 1,000: 4 / 8 / 12 / 16 threads = 41.2 / 32.8 / 33.9 / 34.3 ms)
+            int ranks = 1;
+            if (const char *lw = getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, atoi(lw));
+            n = std::min(8, std::max(2, cpus / 2 / ranks));
         }
         for (int i = 0; i < n; ++i) threads_.emplace_back([this] { loop(); });
     }
@@ -93,11 +101,41 @@ private:
 };
 
 // rows [r0, r1) of an int32 matrix -> uint16 rows of `ld16` elements (padding zeroed); returns the
-// OR of every value seen (any bit at or above 2^16, sign bit included, means "does not fit")
+// OR of every value seen (any bit at or above 2^16, sign bit included, means "does not fit").
+// When source and destination rows are both dense (ld_src == ld16 == n) the chunk is one flat
+// array: 16 values per step, packed with VPACKUSDW and written with non-temporal stores (the
+// staging slot is read next by the DMA engine, never by this core; the chunk starts 32-byte
+// aligned because chunks begin on multiples of 16 rows).
 __attribute__((target("avx2"))) uint32_t narrow_rows_avx2(const int32_t *src, int64_t ld_src, uint16_t *dst,
                                                             int64_t ld16, int64_t r0, int64_t r1, int32_t n)
 {
     uint32_t seen = 0;
+    if (ld_src == n && ld16 == n && ((uintptr_t)dst & 31u) == 0) {
+        const int32_t *s = src + r0 * ld_src;
+        const int64_t total = (r1 - r0) * (int64_t)n;
+        __m256i acc = _mm256_setzero_si256();
+        int64_t i = 0;
+        for (; i + 32 <= total; i += 32) {
+            const __m256i a = _mm256_loadu_si256((const __m256i *)(s + i));
+            const __m256i b = _mm256_loadu_si256((const __m256i *)(s + i + 8));
+            const __m256i c = _mm256_loadu_si256((const __m256i *)(s + i + 16));
+            const __m256i d = _mm256_loadu_si256((const __m256i *)(s + i + 24));
+            acc = _mm256_or_si256(acc, _mm256_or_si256(_mm256_or_si256(a, b), _mm256_or_si256(c, d)));
+            const __m256i lo = _mm256_permute4x64_epi64(_mm256_packus_epi32(a, b), 0xD8);
+            const __m256i hi = _mm256_permute4x64_epi64(_mm256_packus_epi32(c, d), 0xD8);
+            _mm256_stream_si256((__m256i *)(dst + i), lo);
+            _mm256_stream_si256((__m256i *)(dst + i + 16), hi);
+        }
+        alignas(32) uint32_t lanes[8];
+        _mm256_store_si256((__m256i *)lanes, acc);
+        for (int k = 0; k < 8; ++k) seen |= lanes[k];
+        for (; i < total; ++i) {
+            seen |= (uint32_t)s[i];
+            dst[i] = (uint16_t)s[i];
+        }
+        _mm_sfence();
+        return seen;
+    }
     for (int64_t r = r0; r < r1; ++r) {
         const int32_t *s = src + r * ld_src;
         uint16_t *d = dst + (r - r0) * ld16;
@@ -256,8 +294,13 @@ int sd_quant_ps_host(int device, int64_t n_junctions, int32_t n_samples, const i
 
     const int64_t ldd = (n_samples + 3) & ~(int64_t)3;           // device leading dimension
     const int64_t ldm = (n_samples + 15) & ~(int64_t)15;
-    // row blocks of ~32 MB of int32 (tuning knob for experiments: SD_QUANT_HOST_BLOCK_MB)
-    int64_t block_mb = 32;
+    // uint16 staging: on unless SD_QUANT_HOST_U16=0
+    bool use_u16 = true;
+    if (const char *env = getenv("SD_QUANT_HOST_U16")) use_u16 = atoi(env) != 0;
+    // row blocks of ~16 MB of int32 (8 MB on the link as uint16; 32 MB when everything crosses as
+    // int32): 8 / 16 / 32 MB measured 33.4 / 32.8 / 33.3 ms with uint16, 38.6 / 36.4 / 36.3 ms
+    // without.  Tuning knob for experiments: SD_QUANT_HOST_BLOCK_MB
+    int64_t block_mb = use_u16 ? 16 : 32;
     if (const char *env = getenv("SD_QUANT_HOST_BLOCK_MB")) block_mb = std::max<int64_t>(1, atoll(env));
     int64_t block_rows = std::max<int64_t>(64, (block_mb << 20) / (ldd * 4));
     block_rows = (block_rows + 63) & ~(int64_t)63;
@@ -277,9 +320,6 @@ int sd_quant_ps_host(int device, int64_t n_junctions, int32_t n_samples, const i
         need[b] = hi / block_rows;
     }
 
-    // uint16 staging: on unless SD_QUANT_HOST_U16=0; needs at least one worker besides the caller
-    bool use_u16 = true;
-    if (const char *env = getenv("SD_QUANT_HOST_U16")) use_u16 = atoi(env) != 0;
     Workers *workers = use_u16 ? &Workers::get() : nullptr;
     const bool avx2 = __builtin_cpu_supports("avx2");
 
@@ -354,7 +394,7 @@ int sd_quant_ps_host(int device, int64_t n_junctions, int32_t n_samples, const i
         const int64_t r0 = b * block_rows, r1 = std::min(J, r0 + block_rows);
         uint16_t *slot = hp.ring + (size_t)(b % kRingSlots) * (hp.ring_slot_bytes / 2);
         const int parts = std::max(1, workers->size());
-        const int64_t per = (r1 - r0 + parts - 1) / parts;
+        const int64_t per = (((r1 - r0 + parts - 1) / parts) + 15) & ~(int64_t)15;   // chunks start 32-byte aligned
         NarrowJob &job = jobs[b];
         job.pending = (int)((r1 - r0 + per - 1) / per);
         for (int64_t a = r0; a < r1; a += per) {
@@ -367,6 +407,11 @@ int sd_quant_ps_host(int device, int64_t n_junctions, int32_t n_samples, const i
         }
     };
 
+    const bool debug = getenv("SD_HOST_PIPE_DEBUG") != nullptr;
+    using clk = std::chrono::steady_clock;
+    const auto t_begin = clk::now();
+    double wait_narrow_ms = 0, wait_slot_ms = 0;
+    int64_t wide_blocks = 0;
     int64_t next_kernel = 0;
     for (int64_t b = 0; b < n_blocks; ++b) {
         const int64_t r0 = b * block_rows, r1 = std::min(J, r0 + block_rows);
@@ -374,11 +419,16 @@ int sd_quant_ps_host(int device, int64_t n_junctions, int32_t n_samples, const i
         if (use_u16) {
             // keep the narrowing up to kRingSlots - 1 blocks ahead of the copies
             while (submitted < n_blocks && submitted < b + kRingSlots) {
+                const auto t0 = clk::now();
                 if (submitted >= kRingSlots) SD_TRY(cudaEventSynchronize(ev_copy[submitted - kRingSlots]));   // slot free again
+                wait_slot_ms += std::chrono::duration<double, std::milli>(clk::now() - t0).count();
                 submit_narrow(submitted);
                 ++submitted;
             }
+            const auto t0 = clk::now();
             narrow_ok = (jobs[b].wait() >> 16) == 0;
+            wait_narrow_ms += std::chrono::duration<double, std::milli>(clk::now() - t0).count();
+            wide_blocks += narrow_ok ? 0 : 1;
         }
         if (narrow_ok) {
             const uint16_t *slot = hp.ring + (size_t)(b % kRingSlots) * (hp.ring_slot_bytes / 2);
@@ -429,7 +479,15 @@ int sd_quant_ps_host(int device, int64_t n_junctions, int32_t n_samples, const i
     }
 #undef SD_TRY
 #undef SD_TRY_RC
+    const auto t_enqueued = clk::now();
     cleanup();
+    if (debug)
+        fprintf(stderr,
+                "[sd_quant_ps_host] %lld blocks of %lld rows, uint16 %s (%lld blocks sent as int32), %d workers: enqueue "
+                "loop %.2f ms (waiting for narrowing %.2f, for ring slots %.2f), drain %.2f ms\n",
+                (long long)n_blocks, (long long)block_rows, use_u16 ? "on" : "off", (long long)wide_blocks,
+                workers ? workers->size() : 0, std::chrono::duration<double, std::milli>(t_enqueued - t_begin).count(),
+                wait_narrow_ms, wait_slot_ms, std::chrono::duration<double, std::milli>(clk::now() - t_enqueued).count());
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return sd::fail(SD_ERR_CUDA, "sd_quant_ps_host: %s", cudaGetErrorString(e));
     return SD_OK;

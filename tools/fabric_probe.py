@@ -25,7 +25,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     J, S = 400_000, 1000
     nbytes = J * S * 4
-    for chunk_mb in (4, 32, 256):
+    for chunk_mb in (() if "--only-default" in sys.argv else (4, 32, 256)):
         r = bench.fabric_probe(dev, nbytes, nbytes, chunk_mb=chunk_mb, world=world)
         if rank == 0:
             print(json.dumps({"chunk_mb": chunk_mb, **r}), flush=True)
@@ -35,10 +35,10 @@ def main():
         h_counts = torch.empty((J, S), dtype=torch.int32).pin_memory()
         h_counts.copy_(ops.synth_counts(1, 0, J, S, device=dev))
         h_ps = torch.empty((J, S), dtype=torch.float32).pin_memory()
-        for mb in (0, 8, 32, 128):
+        for mb in ((0,) if "--only-default" in sys.argv else (0, 8, 32, 128)):
             if mb:
                 os.environ["SD_QUANT_HOST_BLOCK_MB"] = str(mb)
-            else:
+            elif "--only-default" not in sys.argv:
                 os.environ.pop("SD_QUANT_HOST_BLOCK_MB", None)
             ops.quant_ps_host(h_counts, rp, ci, out=h_ps, device=local)
             ts = []
