@@ -189,10 +189,15 @@ int sd_fisher_tables(int64_t n_tables, const int64_t *a, const int64_t *b,
  * statsmodels multipletests(method="fdr_bh")[1] applied to every column ("pairwise", the CLI
  * default; SD_BH_COLUMNS) or to the flattened matrix ("all"; SD_BH_ALL).  For the n values of a
  * segment sorted ascending,  adj_(k) = min(1, min_{m >= k} p_(m) / (m / n))  with both divisions
- * in IEEE binary64, so results are bit-identical to the numpy expression statsmodels evaluates.
+ * in IEEE binary64, so results are bit-identical to the numpy restatement of statsmodels'
+ * fdrcorrection (oracle/oracle_np.py; statsmodels itself is not installable here -- the
+ * restatement is pinned to scipy.stats.false_discovery_control within 2 ulp, tests/test_bh_pin.py).
  * p / out: DEVICE matrices [n_rows, n_cols] (out may alias p); at most 2^31 - 1 values per call
- * (SD_ERR_UNSUPPORTED beyond: column blocks are independent, split them).  Asynchronous on
- * `stream`; scratch comes from a caller-provided device workspace (~33 bytes per value).
+ * (SD_ERR_UNSUPPORTED beyond: column blocks are independent, split them).  Scratch comes from a
+ * caller-provided device workspace (~33 bytes per value).  SD_BH_ALL is asynchronous on `stream`;
+ * SD_BH_COLUMNS with 8,192..524,288 rows runs a per-column sample sort and synchronises `stream`
+ * once before returning (it reads back one flag that says whether the sampled splitters produced
+ * a bucket too large to sort on chip; if so the call repeats with the global radix sort).
  */
 #define SD_BH_COLUMNS 0
 #define SD_BH_ALL 1

@@ -294,8 +294,15 @@ int sd_quant_ps_host(int device, int64_t n_junctions, int32_t n_samples, const i
 
     const int64_t ldd = (n_samples + 3) & ~(int64_t)3;           // device leading dimension
     const int64_t ldm = (n_samples + 15) & ~(int64_t)15;
-    // uint16 staging: on unless SD_QUANT_HOST_U16=0
+    // uint16 staging pays when the PCIe link is the bottleneck, i.e. when this process has the host's
+    // memory system to itself: one B200 behind a 16-vCPU host moves 1.6 GB each way in 32.7 ms with it
+    // against 36.4 ms without (D2H alone: 28.2 ms).  When several ranks share the host the combined
+    // DMA traffic already saturates host memory (two GPUs: 131 GB/s duplex against 97 for one) and the
+    // narrowing's extra reads and writes make it worse (60 against 48.9 ms, which IS the two-GPU
+    // duplex ceiling), so ranks of a multi-GPU job (LOCAL_WORLD_SIZE > 1) send int32.
+    // SD_QUANT_HOST_U16=0/1 overrides either way.
     bool use_u16 = true;
+    if (const char *lw = getenv("LOCAL_WORLD_SIZE")) use_u16 = atoi(lw) <= 1;
     if (const char *env = getenv("SD_QUANT_HOST_U16")) use_u16 = atoi(env) != 0;
     // row blocks of ~16 MB of int32 (8 MB on the link as uint16; 32 MB when everything crosses as
     // int32): 8 / 16 / 32 MB measured 33.4 / 32.8 / 33.3 ms with uint16, 38.6 / 36.4 / 36.3 ms
@@ -411,14 +418,21 @@ int sd_quant_ps_host(int device, int64_t n_junctions, int32_t n_samples, const i
     using clk = std::chrono::steady_clock;
     const auto t_begin = clk::now();
     double wait_narrow_ms = 0, wait_slot_ms = 0;
+    bool narrowing = use_u16;
     int64_t wide_blocks = 0;
     int64_t next_kernel = 0;
     for (int64_t b = 0; b < n_blocks; ++b) {
         const int64_t r0 = b * block_rows, r1 = std::min(J, r0 + block_rows);
         bool narrow_ok = false;
-        if (use_u16) {
+        // guard: if the link keeps waiting for the narrowing threads (CPUs busy elsewhere), the
+        // remaining blocks cross as int32 straight from the caller's buffer
+        if (use_u16 && narrowing && b >= 8) {
+            const double elapsed = std::chrono::duration<double, std::milli>(clk::now() - t_begin).count();
+            if (wait_narrow_ms > 0.5 * elapsed) narrowing = false;
+        }
+        if (use_u16 && (narrowing || b < submitted)) {
             // keep the narrowing up to kRingSlots - 1 blocks ahead of the copies
-            while (submitted < n_blocks && submitted < b + kRingSlots) {
+            while (narrowing && submitted < n_blocks && submitted < b + kRingSlots) {
                 const auto t0 = clk::now();
                 if (submitted >= kRingSlots) SD_TRY(cudaEventSynchronize(ev_copy[submitted - kRingSlots]));   // slot free again
                 wait_slot_ms += std::chrono::duration<double, std::milli>(clk::now() - t0).count();
@@ -428,7 +442,6 @@ int sd_quant_ps_host(int device, int64_t n_junctions, int32_t n_samples, const i
             const auto t0 = clk::now();
             narrow_ok = (jobs[b].wait() >> 16) == 0;
             wait_narrow_ms += std::chrono::duration<double, std::milli>(clk::now() - t0).count();
-            wide_blocks += narrow_ok ? 0 : 1;
         }
         if (narrow_ok) {
             const uint16_t *slot = hp.ring + (size_t)(b % kRingSlots) * (hp.ring_slot_bytes / 2);
@@ -448,6 +461,7 @@ int sd_quant_ps_host(int device, int64_t n_junctions, int32_t n_samples, const i
                                          (size_t)ld_counts * 4, (size_t)n_samples * 4, (size_t)(r1 - r0),
                                          cudaMemcpyHostToDevice, s_in));
             if (use_u16) SD_TRY(cudaEventRecord(ev_copy[b], s_in));
+            wide_blocks += use_u16 ? 1 : 0;
         }
         if (low_mask)
             SD_TRY(cudaMemcpy2DAsync(d_mask + r0 * ldm, (size_t)ldm, low_mask + r0 * ld_mask, (size_t)ld_mask,

@@ -52,6 +52,61 @@ def test_columns_and_all_bit_exact(shape, kind):
     assert np.array_equal(d.cpu().numpy(), p)           # input untouched when out is separate
 
 
+@pytest.mark.parametrize("kind", ["uniform", "ties", "wide", "fisher"])
+@pytest.mark.parametrize("shape", [(8192, 3), (8193, 40), (50_000, 33), (200_000, 7), (524_288, 2), (524_289, 2)])
+def test_column_sample_sort_bit_exact(shape, kind, monkeypatch):
+    """Column mode from 8,192 rows up runs the per-column sample sort (splitters from a sample,
+    equality buckets, windows sorted in shared memory): bit-identical to the oracle and to the
+    global-sort path, on uniform values, on a handful of distinct values (every bucket an equality
+    bucket, p = 1 filling a third of the column), on values spread over 300 decades, and on a
+    Fisher-like mix (8 % exact ones, the rest beta-distributed with heavy ties at small values);
+    524,289 rows is the first shape past the sample sort's range."""
+    _, ops = _ops()
+    rng = np.random.default_rng(shape[0] + shape[1])
+    if kind == "fisher":
+        p = np.minimum(1.0, rng.beta(0.4, 1.0, size=shape))
+        p[rng.random(shape) < 0.08] = 1.0
+        small = rng.random(shape) < 0.1
+        p[small] = np.round(p[small], 2)                      # ties away from the splitters
+    else:
+        p = _pvalues(rng, shape, kind)
+    d = torch.from_numpy(p).cuda()
+    want = _want(p, "pairwise")
+    got = ops.bh_adjust(d, "pairwise").cpu().numpy()
+    assert np.array_equal(_bits(got), _bits(want)), (shape, kind)
+    monkeypatch.setenv("SD_BH_GLOBAL_SORT", "1")
+    other = ops.bh_adjust(d, "pairwise").cpu().numpy()
+    assert np.array_equal(_bits(other), _bits(want))
+    monkeypatch.delenv("SD_BH_GLOBAL_SORT")
+    monkeypatch.setenv("SD_BH_TEST_FAIL", "1")                # the oversize-bucket flag: repeat with the global sort
+    again = ops.bh_adjust(d, "pairwise").cpu().numpy()
+    assert np.array_equal(_bits(again), _bits(want))
+    monkeypatch.delenv("SD_BH_TEST_FAIL")
+    work = d.clone()                                          # in place
+    ops.bh_adjust(work, "pairwise", out=work)
+    assert np.array_equal(_bits(work.cpu().numpy()), _bits(want))
+
+
+def test_column_sample_sort_nan_and_padded_views():
+    _, ops = _ops()
+    rng = np.random.default_rng(77)
+    p = rng.random((20_000, 5))
+    p[rng.integers(0, 20_000, 30), 1] = np.nan               # one column with NaNs: the whole column turns NaN-ish like numpy
+    p[:, 3] = 1.0
+    p[:, 4] = 0.0
+    with np.errstate(invalid="ignore"):
+        want = _want(p, "pairwise")
+    buf = torch.full((20_000, 8), -3.0, dtype=torch.float64, device="cuda")
+    buf[:, 2:7] = torch.from_numpy(p).cuda()
+    view = buf[:, 2:7]
+    got = ops.bh_adjust(view, "pairwise").cpu().numpy()
+    for k in range(5):
+        assert np.array_equal(np.isnan(got[:, k]), np.isnan(want[:, k])), k
+        ok = ~np.isnan(want[:, k])
+        assert np.array_equal(_bits(got[ok, k]), _bits(want[ok, k])), k
+    assert (buf[:, :2] == -3.0).all() and (buf[:, 7:] == -3.0).all()
+
+
 def test_long_segments_cross_many_chunks():
     """One segment of 3,000,001 values: > 256 chunks, so the per-segment carry scan loops."""
     _, ops = _ops()

@@ -20,8 +20,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    import torch.distributed as dist
     if world > 1:
-        import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     J, S = 400_000, 1000
     nbytes = J * S * 4
@@ -35,19 +35,28 @@ def main():
         h_counts = torch.empty((J, S), dtype=torch.int32).pin_memory()
         h_counts.copy_(ops.synth_counts(1, 0, J, S, device=dev))
         h_ps = torch.empty((J, S), dtype=torch.float32).pin_memory()
-        for mb in ((0,) if "--only-default" in sys.argv else (0, 8, 32, 128)):
-            if mb:
+        modes = [("1", 16), ("1", 32), ("0", 16), ("0", 32), ("0", 128)] if "--modes" in sys.argv else [(None, 0)]
+        for u16, mb in modes:
+            if u16 is not None:
+                os.environ["SD_QUANT_HOST_U16"] = u16
                 os.environ["SD_QUANT_HOST_BLOCK_MB"] = str(mb)
-            elif "--only-default" not in sys.argv:
-                os.environ.pop("SD_QUANT_HOST_BLOCK_MB", None)
             ops.quant_ps_host(h_counts, rp, ci, out=h_ps, device=local)
             ts = []
             for _ in range(5):
+                torch.cuda.synchronize()
+                if world > 1:
+                    dist.barrier()
                 t0 = time.perf_counter()
                 ops.quant_ps_host(h_counts, rp, ci, out=h_ps, device=local)
-                ts.append(time.perf_counter() - t0)
+                dt = time.perf_counter() - t0
+                if world > 1:
+                    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    dt = float(t.item())
+                ts.append(dt)
             if rank == 0:
-                print(json.dumps({"sd_quant_ps_host_block_mb": mb or "default", "ms": [round(t * 1e3, 2) for t in ts]}), flush=True)
+                print(json.dumps({"sd_quant_ps_host": {"u16": u16, "block_mb": mb or "default"}, "n_gpus": world,
+                                  "ms_max_over_ranks": [round(t * 1e3, 2) for t in ts]}), flush=True)
 
 
 if __name__ == "__main__":
