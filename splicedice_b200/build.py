@@ -52,6 +52,32 @@ def stale() -> bool:
     return any(os.path.getmtime(f) > t for f in _deps())
 
 
+def build_variant(tag: str, extra_flags) -> str:
+    """An experiment build: every source recompiled with ``extra_flags`` (e.g. ``-DSD_FISHER_CUT_BITS=36``)
+    into ``_lib/libsplicedice_b200.<tag>.so``; ``SPLICEDICE_B200_LIB=<that path>`` makes native.load() use it."""
+    cc = nvcc()
+    if cc is None:
+        raise RuntimeError("nvcc not found")
+    obj_dir = os.path.join(OUT_DIR, f"obj_{tag}")
+    os.makedirs(obj_dir, exist_ok=True)
+
+    def compile_one(src):
+        obj = os.path.join(obj_dir, os.path.basename(src) + ".o")
+        r = subprocess.run([cc, *NVCC_FLAGS, *extra_flags, "-c", src, "-o", obj], capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError(f"nvcc failed on {src}")
+        return obj
+
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        objs = list(ex.map(compile_one, sources()))
+    lib = os.path.join(OUT_DIR, f"libsplicedice_b200.{tag}.so")
+    subprocess.run([cc, "-shared", "-o", lib, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
+                    "-Xcompiler", "-fPIC", "-cudart", "static", "-lquadmath"], check=True)
+    shutil.rmtree(obj_dir)
+    return lib
+
+
 def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) -> str:
     if not force and not stale():
         return LIB

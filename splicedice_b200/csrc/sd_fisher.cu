@@ -160,7 +160,7 @@ __device__ __forceinline__ int cost_bucket(int a, int b, int c, int d)
     const float var = fmaxf((n * rN) * (n1 * rN) * (n2 * (N - n)) * __fdividef(1.f, fmaxf(N - 1.f, 1.f)), 1e-6f);
     const float inv_sig = rsqrtf(var);
     const float z = fabsf(fa - mode) * inv_sig;
-    const float t = fmaf(z, z, 66.5f);
+    const float t = fmaf(z, z, 1.3863f * (float)fisher::kCutBits);    // 2 ln 2^kCutBits
     const float terms = var * inv_sig * (t * rsqrtf(t) - z);
     return min(kBinBuckets - 1, 1 + (int)(6.0f * __log2f(1.0f + terms)));
 }

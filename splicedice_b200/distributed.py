@@ -95,11 +95,14 @@ def sharded_rows(counts, row_ptr, col_idx, slab_fn, gather=True, weights=None):
 
 def quant_ps_sharded(counts_host, row_ptr, col_idx, device=None, gather=True, low_mask=None):
     """PS of a host int32 count matrix with the rows split over the ranks' GPUs.  Rank r uploads
-    only its slab.  Returns the full float32 matrix on every rank's GPU (``gather``) or the local
-    slab and its row range."""
+    only its slab (and its slab of the low-coverage mask: the NaN overwrite of SPLICEDICE.py:307-309
+    is per cell, so it shards with the rows).  Returns the full float32 matrix on every rank's GPU
+    (``gather``) or the local slab and its row range."""
     from . import ops
     rank, _ = _world()
     dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+    n_cols = counts_host.shape[1]
+    parts = sharding.partition_rows(row_ptr, col_idx, _world()[1], sharding.row_weights(row_ptr, n_cols))
 
     def slab(counts_slab, rp, ci):
         c = torch.from_numpy(np.ascontiguousarray(counts_slab, dtype=np.int32)).to(dev)
@@ -108,10 +111,12 @@ def quant_ps_sharded(counts_host, row_ptr, col_idx, device=None, gather=True, lo
             buf = torch.zeros((c.shape[0], (n + 3) // 4 * 4), dtype=torch.int32, device=dev)
             buf[:, :n] = c
             c = buf[:, :n]
-        return ops.quant_ps(c, rp, ci, want_f32=True)["ps_f32"]
+        mask = None
+        if low_mask is not None:
+            r0, r1 = parts[rank]
+            mask = torch.from_numpy(np.ascontiguousarray(low_mask[r0:r1], dtype=np.uint8)).to(dev)
+        return ops.quant_ps(c, rp, ci, low_mask=mask, want_f32=True)["ps_f32"]
 
-    if low_mask is not None:
-        raise NotImplementedError("low_mask is applied per slab by the caller")
     return sharded_rows(counts_host, row_ptr, col_idx, slab, gather=gather)
 
 
@@ -191,8 +196,6 @@ def pairwise_sharded(counts_host, row_ptr, col_idx, correction="pairwise", devic
     rank, world = _world()
     if correction not in ("none", "pairwise", "all"):
         raise ValueError("correction must be 'none', 'pairwise' or 'all'")
-    if correction == "all" and world > 1:
-        raise NotImplementedError("'all' ranks every p-value of the matrix together: run it on one GPU")
     dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
     parts = sharding.partition_rows(row_ptr, col_idx, world)
     r0, r1 = parts[rank]
@@ -200,6 +203,8 @@ def pairwise_sharded(counts_host, row_ptr, col_idx, correction="pairwise", devic
     slab = np.ascontiguousarray(counts_host[r0:r1]).astype(np.int64)
     if (slab < 0).any():
         raise ValueError("All values in `table` must be nonnegative.")
+    if (slab >= 2 ** 31).any():                     # the same guard pairwise_fisher.pairwise_pvalues has
+        raise ValueError("counts of 2^31 and above are not supported")
     S = slab.shape[1]
     buf = torch.zeros((r1 - r0, (S + 3) // 4 * 4), dtype=torch.int32, device=dev)
     buf[:, :S] = torch.from_numpy(slab.astype(np.int32)).to(dev)
@@ -211,5 +216,10 @@ def pairwise_sharded(counts_host, row_ptr, col_idx, correction="pairwise", devic
     if correction == "pairwise":
         p = bh_columns_sharded(p, parts, lambda cols: ops.bh_adjust(cols, "pairwise", out=cols))
     elif correction == "all":
-        ops.bh_adjust(p, "all", out=p)
+        # one ranking over every p-value of the matrix (pairwise_fisher.py:189-191): the row slabs are
+        # gathered on every GPU (NCCL), each adjusts the whole matrix and keeps its own rows -- the
+        # matrix has to fit one GPU for this mode anyway (sd_bh_adjust: < 2^31 values per segment)
+        full = all_gather_rows(p, parts) if world > 1 else p
+        ops.bh_adjust(full, "all", out=full)
+        p = full[r0:r1].clone() if world > 1 else full
     return p, (r0, r1)

@@ -100,8 +100,11 @@ def load():
     if _lib is not None:
         return _lib
     path = _build.LIB
+    override = os.environ.get("SPLICEDICE_B200_LIB")          # experiment builds (build.build_variant)
     try:
-        if _build.nvcc() is not None:
+        if override:
+            path = override
+        elif _build.nvcc() is not None:
             path = _build.build()
     except Exception as e:  # build failure is fatal: there is nothing to fall back to
         raise NativeLibraryError(f"cannot build libsplicedice_b200.so: {e}") from e

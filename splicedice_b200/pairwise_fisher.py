@@ -58,7 +58,7 @@ def sample_pairs(n_samples):
     return [(i, j) for i in range(n_samples - 1) for j in range(i + 1, n_samples)]
 
 
-def pairwise_pvalues(events, counts, clusters, device=0, correction="none"):
+def pairwise_pvalues(events, counts, clusters, device=0, correction="none", gpus=1):
     """float64[len(events), n_pairs] two-sided Fisher p-values, pair order as ``sample_pairs``;
     ``correction`` = 'none' | 'pairwise' | 'all' applies Benjamini-Hochberg on the device before
     the matrix comes back (pairwise_fisher.py:182-191)."""
@@ -74,6 +74,9 @@ def pairwise_pvalues(events, counts, clusters, device=0, correction="none"):
     if (as_int >= 2 ** 31).any():
         raise ValueError("counts of 2^31 and above are not supported")
     row_ptr, col_idx = jn.csr_from_named_lists(events, clusters, "isin")
+    if gpus > 1:                                    # one worker process per GPU (row slabs; NCCL for the correction)
+        from . import multigpu
+        return multigpu.pairwise(as_int, row_ptr, col_idx, len(pairs), correction=correction, n_gpus=gpus)
     dev = torch.device("cuda", device)
     S = n_samples
     buf = torch.zeros((n_events, (S + 3) // 4 * 4), dtype=torch.int32, device=dev)
@@ -101,6 +104,8 @@ def add_parser(parser):
     parser.add_argument("-f", "--filter_list", help="text file of events to analyse, one per line")
     parser.add_argument("-o", "--output", default="pairwise.tsv", help="output TSV")
     parser.add_argument("--device", type=int, default=0, help="CUDA device ordinal")
+    parser.add_argument("--gpus", type=int, default=1,
+                        help="GPUs: one worker process per GPU on devices 0..N-1, events cut into row slabs")
 
 
 def run_with(args):
@@ -119,7 +124,7 @@ def run_with(args):
     print("Analyzing pairs:")
     print(",".join(columns))
     parray = pairwise_pvalues(events, counts, clusters, getattr(args, "device", 0),
-                              correction=args.multiple_test_correction)
+                              correction=args.multiple_test_correction, gpus=getattr(args, "gpus", 1))
     print(f"[{len(events)} / {len(events)}] events analyzed...")
     from . import textio
     textio.write_matrix(args.output, "clusterID\t" + "\t".join(columns) + "\n", events,

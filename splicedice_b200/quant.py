@@ -159,8 +159,9 @@ class SPLICEDICE:
     """The quant pipeline.  Constructing it runs every stage, like the reference class; pass
     ``run=False`` to drive the stages by hand (tests, library use)."""
 
-    def __init__(self, manifestFilename, outputPrefix, args, device=0, run=True, native_io=True):
+    def __init__(self, manifestFilename, outputPrefix, args, device=0, run=True, native_io=True, gpus=1):
         self.args = args
+        self.gpus = gpus
         self.native_io = native_io
         self.manifestFilename = manifestFilename
         self.outputPrefix = outputPrefix
@@ -350,6 +351,10 @@ class SPLICEDICE:
         row_ptr, col_idx = self._csr
         if self.counts.size == 0:
             return np.zeros(self.counts.shape, dtype=np.float32)
+        if self.gpus > 1:                           # one worker process per GPU, row slabs at cluster boundaries
+            from . import multigpu
+            return multigpu.quant_ps(np.ascontiguousarray(self.counts, dtype=np.int32), row_ptr, col_idx,
+                                     low_mask=mask, n_gpus=self.gpus)
         return ops.quant_ps_host(np.ascontiguousarray(self.counts, dtype=np.int32), row_ptr, col_idx,
                                  low_mask=mask, device=self.device).numpy()
 
@@ -422,6 +427,8 @@ def add_parser(parser):
     parser.add_argument("--lowCoverageNan", action="store_true", help="NaN for cells scored below minUnique")
     parser.add_argument("--minEntropy", type=float, default=1, help="least Shannon diversity of read offsets")
     parser.add_argument("--device", type=int, default=0, help="CUDA device ordinal")
+    parser.add_argument("--gpus", type=int, default=1,
+                        help="GPUs for the PS stage: one worker process per GPU on devices 0..N-1, rows cut at cluster boundaries")
     parser.add_argument("--threads", type=int, default=0, help="host threads for file parsing (0 = all)")
     parser.add_argument("--pythonIO", action="store_true", help="read the sample files with the plain python parser")
     parser.add_argument("--npz", action="store_true",
@@ -430,7 +437,7 @@ def add_parser(parser):
 
 def run_with(args):
     SPLICEDICE(args.manifest, args.output_prefix, args, device=getattr(args, "device", 0),
-               native_io=not getattr(args, "pythonIO", False))
+               native_io=not getattr(args, "pythonIO", False), gpus=getattr(args, "gpus", 1))
 
 
 if __name__ == "__main__":
