@@ -14,7 +14,9 @@
 // (:247-254); the priors come out of a radix sort of the (k, b) edge list on (k asc, b desc).
 // All ids written to row_ptr / col_idx are OUTPUT rows (tuple order (chrom, start, end, strand)).
 //
-// Device-wide sort / scan primitives are CUB's; everything else is a kernel below.
+// The output row order needs no sort of its own (k_out_rank).  Device-wide sort / scan primitives
+// are CUB's (two radix sorts for the cluster order, one for the prior lists, five scans); everything
+// else is a kernel below.  One host synchronisation per call (nnz, component count, overflow check).
 #include <cub/cub.cuh>
 
 #include <algorithm>
@@ -47,26 +49,59 @@ __global__ void k_key_cluster(int64_t n, const int32_t *order, const int32_t *ch
 {
     SD_GRID_STRIDE(i, n) { int32_t j = order[i]; key[i] = seg_key(chrom[j], strand[j], start[j]); }
 }
-// output-order keys: pass 1 (end, strand), pass 2 (chrom, start)
-__global__ void k_key_out1(int64_t n, const int32_t *end, const int32_t *strand, uint64_t *key, int32_t *val)
+// Output row (the rank under tuple order (chrom, start, end, strand), SPLICEDICE.py:96) of the
+// junction at every cluster-order position, without another sort: cluster order is (chrom, strand,
+// start, end), so inside one chromosome the output order is the merge of that chromosome's strand
+// segments, each already sorted by (start, end).  The rank of a junction is the first position of
+// its chromosome plus, for every strand segment of the chromosome, the number of its junctions
+// that come before this one -- one binary search per segment (junctions are distinct, so the only
+// ties are across strands and break on the strand rank).
+__device__ __forceinline__ int64_t first_at_least(const uint64_t *key, int64_t lo, int64_t hi, uint64_t probe)
+{
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (key[mid] < probe) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+__global__ void k_out_rank(int64_t n, const int32_t *order, const uint64_t *key_sorted, const int32_t *end,
+                           int32_t *out_row, int32_t *row_of_pos)
 {
     SD_GRID_STRIDE(i, n)
     {
-        key[i] = ((uint64_t)(uint32_t)end[i] << 8) | (uint64_t)(uint32_t)(strand[i] & 0xFF);
-        val[i] = (int32_t)i;
+        const uint64_t key = key_sorted[i];
+        const uint64_t chrom = key >> 39;
+        const uint32_t strand = (uint32_t)(key >> 31) & 0xFFu, start = (uint32_t)key & 0x7FFFFFFFu;
+        const int32_t j = order[i];
+        const uint32_t my_end = (uint32_t)end[j];
+        const int64_t c_lo = first_at_least(key_sorted, 0, i + 1, chrom << 39);
+        const int64_t c_hi = first_at_least(key_sorted, i + 1, n, (chrom + 1) << 39);
+        int64_t rank = c_lo;
+        for (int64_t pos = c_lo; pos < c_hi;) {
+            const uint32_t s2 = (uint32_t)(key_sorted[pos] >> 31) & 0xFFu;
+            const int64_t seg_end = first_at_least(key_sorted, pos + 1, c_hi, (chrom << 39) | ((uint64_t)(s2 + 1) << 31));
+            if (s2 == strand) {
+                rank += i - pos;                                  // own segment: everything before this position
+            } else {
+                // first position of the segment that does not come before (start, my_end, strand)
+                int64_t lo = pos, hi = seg_end;
+                while (lo < hi) {
+                    const int64_t mid = (lo + hi) >> 1;
+                    const uint32_t st = (uint32_t)key_sorted[mid] & 0x7FFFFFFFu;
+                    bool before = st < start;
+                    if (st == start) {
+                        const uint32_t en = (uint32_t)end[order[mid]];
+                        before = en < my_end || (en == my_end && s2 < strand);
+                    }
+                    if (before) lo = mid + 1; else hi = mid;
+                }
+                rank += lo - pos;
+            }
+            pos = seg_end;
+        }
+        out_row[j] = (int32_t)rank;
+        row_of_pos[i] = (int32_t)rank;
     }
-}
-__global__ void k_key_out2(int64_t n, const int32_t *order, const int32_t *chrom, const int32_t *start, uint64_t *key)
-{
-    SD_GRID_STRIDE(i, n)
-    {
-        int32_t j = order[i];
-        key[i] = ((uint64_t)(uint32_t)chrom[j] << 31) | (uint64_t)(uint32_t)start[j];
-    }
-}
-__global__ void k_invert(int64_t n, const int32_t *perm, int32_t *inv)
-{
-    SD_GRID_STRIDE(i, n) inv[perm[i]] = (int32_t)i;
 }
 
 struct SegMax {
@@ -85,8 +120,7 @@ struct SegMaxOp {
 
 // per position: later-neighbour run, segment heads, scan input, difference array
 __global__ void k_sweep(int64_t n, const int32_t *order, const uint64_t *key_sorted, const int32_t *chrom,
-                        const int32_t *strand, const int32_t *end, const int32_t *out_row, int32_t *row_of_pos,
-                        int32_t *n_later, int32_t *diff, SegMax *seg_in)
+                        const int32_t *strand, const int32_t *end, int32_t *n_later, int32_t *diff, SegMax *seg_in)
 {
     SD_GRID_STRIDE(i, n)
     {
@@ -104,7 +138,6 @@ __global__ void k_sweep(int64_t n, const int32_t *order, const uint64_t *key_sor
             atomicAdd(diff + i + 1, 1);
             atomicAdd(diff + i + 1 + later, -1);
         }
-        row_of_pos[i] = out_row[j];
         const bool head = i == 0 || (key_sorted[i] >> 31) != (key_sorted[i - 1] >> 31);
         seg_in[i].head = head ? 1 : 0;
         seg_in[i].val = end[j];
@@ -293,13 +326,6 @@ int sd_cluster_build(int64_t n, const int32_t *chrom_rank, const int32_t *strand
     const int g = grid_for(n);
     const int ni = (int)n;
 
-    // ---- output row order: stable LSD sort, (end, strand) then (chrom, start) ------------
-    k_key_out1<<<g, kBlock, 0, stream>>>(n, end, strand_rank, key_a, val_a);
-    SD_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(cub_ws, cub_b, key_a, key_b, val_a, val_b, ni, 0, 40, stream));
-    k_key_out2<<<g, kBlock, 0, stream>>>(n, val_b, chrom_rank, start, key_a);
-    SD_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(cub_ws, cub_b, key_a, key_b, val_b, val_a, ni, 0, 56, stream));
-    k_invert<<<g, kBlock, 0, stream>>>(n, val_a, out_row);
-
     // ---- cluster order: stable LSD sort, end then (chrom, strand, start) ------------------
     uint32_t *key32_a = (uint32_t *)key_a, *key32_b = (uint32_t *)key_b;
     k_iota_end<<<g, kBlock, 0, stream>>>(n, end, key32_a, val_a);
@@ -307,26 +333,24 @@ int sd_cluster_build(int64_t n, const int32_t *chrom_rank, const int32_t *strand
     k_key_cluster<<<g, kBlock, 0, stream>>>(n, val_b, chrom_rank, strand_rank, start, key_a);
     SD_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(cub_ws, cub_b, key_a, key_b, val_b, cluster_order, ni, 0, 64, stream));
     // key_b = sorted (chrom, strand, start) keys
+    // ---- output row order from the cluster order (merge ranks, no sort) --------------------
+    k_out_rank<<<g, kBlock, 0, stream>>>(n, cluster_order, key_b, end, out_row, row_of_pos);
 
     // ---- sweep ----------------------------------------------------------------------------
     SD_CHECK_CUDA(cudaMemsetAsync(diff, 0, (size_t)(n + 1) * 4, stream));
-    k_sweep<<<g, kBlock, 0, stream>>>(n, cluster_order, key_b, chrom_rank, strand_rank, end, out_row, row_of_pos,
-                                      n_later, diff, seg_in);
+    k_sweep<<<g, kBlock, 0, stream>>>(n, cluster_order, key_b, chrom_rank, strand_rank, end, n_later, diff, seg_in);
     SD_CHECK_CUDA(cub::DeviceScan::InclusiveSum(cub_ws, cub_b, (const int32_t *)diff, n_prior, ni + 1, stream));
     SD_CHECK_CUDA(cub::DeviceScan::InclusiveScan(cub_ws, cub_b, (const SegMax *)seg_in, seg_out, SegMaxOp(), ni, stream));
     k_comp_head<<<g, kBlock, 0, stream>>>(n, key_b, seg_out, val_a);
     SD_CHECK_CUDA(cub::DeviceScan::InclusiveSum(cub_ws, cub_b, (const int32_t *)val_a, comp_id, ni, stream));
     k_comp_id<<<g, kBlock, 0, stream>>>(n, comp_id);
 
-    // 64-bit edge count first: the int32 CSR cannot hold more than 2^31 - 1 entries
+    // 64-bit edge count (the int32 CSR cannot hold more than 2^31 - 1 entries): read back together
+    // with nnz and the component count in the call's single synchronisation -- an overflowing
+    // prefix sum below only produces garbage that is never returned
     unsigned long long *d_edges = (unsigned long long *)diff;      // diff is dead after the prefix sum
     SD_CHECK_CUDA(cudaMemsetAsync(d_edges, 0, 8, stream));
     k_sum64<<<g, kBlock, 0, stream>>>(n, n_later, d_edges);
-    unsigned long long h_edges = 0;
-    SD_CHECK_CUDA(cudaMemcpyAsync(&h_edges, d_edges, 8, cudaMemcpyDeviceToHost, stream));
-    SD_CHECK_CUDA(cudaStreamSynchronize(stream));
-    if (2 * h_edges > 0x7FFFFFFFull)
-        return fail(SD_ERR_OVERFLOW, "sd_cluster_build: %llu adjacency entries do not fit int32 indices", 2 * h_edges);
 
     // ---- CSR row pointer in output-row space -----------------------------------------------
     SD_CHECK_CUDA(cudaMemsetAsync(deg_row + n, 0, 4, stream));
@@ -334,10 +358,14 @@ int sd_cluster_build(int64_t n, const int32_t *chrom_rank, const int32_t *strand
     SD_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(cub_ws, cub_b, (const int32_t *)deg_row, row_ptr, ni + 1, stream));
     if (int rc = check_launch("sd_cluster_build kernels")) return rc;
 
+    unsigned long long h_edges = 0;
     int32_t h_nnz = 0, h_comp = 0;
+    SD_CHECK_CUDA(cudaMemcpyAsync(&h_edges, d_edges, 8, cudaMemcpyDeviceToHost, stream));
     SD_CHECK_CUDA(cudaMemcpyAsync(&h_nnz, row_ptr + n, 4, cudaMemcpyDeviceToHost, stream));
     SD_CHECK_CUDA(cudaMemcpyAsync(&h_comp, comp_id + (n - 1), 4, cudaMemcpyDeviceToHost, stream));
     SD_CHECK_CUDA(cudaStreamSynchronize(stream));
+    if (2 * h_edges > 0x7FFFFFFFull)
+        return fail(SD_ERR_OVERFLOW, "sd_cluster_build: %llu adjacency entries do not fit int32 indices", 2 * h_edges);
     *nnz_host = h_nnz;
     *n_components_host = (int64_t)h_comp + 1;
     return SD_OK;
