@@ -189,6 +189,8 @@ struct HostPipe {
     std::vector<cudaEvent_t> events;
     uint16_t *ring = nullptr;          // pinned staging, kRingSlots slots
     size_t ring_slot_bytes = 0;
+    double ms_per_mb[2] = {0, 0};      // last large call as int32 [0] / uint16 [1]: the format autotuner
+    long tune_calls = 0;
 };
 HostPipe g_pipe[kMaxDevices];
 
@@ -249,6 +251,7 @@ struct NarrowJob {
         cv.wait(lock, [this] { return pending == 0; });
         return seen;
     }
+
 };
 
 }  // namespace
@@ -294,16 +297,36 @@ int sd_quant_ps_host(int device, int64_t n_junctions, int32_t n_samples, const i
 
     const int64_t ldd = (n_samples + 3) & ~(int64_t)3;           // device leading dimension
     const int64_t ldm = (n_samples + 15) & ~(int64_t)15;
-    // uint16 staging pays when the PCIe link is the bottleneck, i.e. when this process has the host's
-    // memory system to itself: one B200 behind a 16-vCPU host moves 1.6 GB each way in 32.7 ms with it
-    // against 36.4 ms without (D2H alone: 28.2 ms).  When several ranks share the host the combined
-    // DMA traffic already saturates host memory (two GPUs: 131 GB/s duplex against 97 for one) and the
-    // narrowing's extra reads and writes make it worse (60 against 48.9 ms, which IS the two-GPU
-    // duplex ceiling), so ranks of a multi-GPU job (LOCAL_WORLD_SIZE > 1) send int32.
-    // SD_QUANT_HOST_U16=0/1 overrides either way.
-    bool use_u16 = true;
-    if (const char *lw = getenv("LOCAL_WORLD_SIZE")) use_u16 = atoi(lw) <= 1;
-    if (const char *env = getenv("SD_QUANT_HOST_U16")) use_u16 = atoi(env) != 0;
+    // The link format.  uint16 staging halves the H2D bytes at the price of one pass of host threads
+    // over the matrix (1.6 GB read + 0.8 GB written at 400,000 x 1,000).  Whether that pays depends on
+    // the host: on one 16-vCPU B200 box it took 32.7 ms against 36.4 ms for plain int32 (duplex
+    // ceiling of the same bytes 33.1 ms, D2H alone 28.2 ms); on two other boxes of the same pool the
+    // host threads slowed the copy-back stream and it took 40-42 ms against 35.7; with two ranks
+    // sharing a host it loses outright (60 against 48.9 ms, which IS the two-GPU duplex ceiling).  So
+    // the format is chosen by measurement: ranks of a multi-GPU job (LOCAL_WORLD_SIZE > 1) and small
+    // matrices send int32; otherwise the per-device context times its first large call in each
+    // format and keeps the faster one, trying the other again every 32nd call.  SD_QUANT_HOST_U16=0/1
+    // overrides.  Results never depend on the format.
+    HostPipe &hp = g_pipe[device];
+    std::lock_guard<std::mutex> pipe_lock(hp.mu);
+    const double cells_mb = (double)J * n_samples * 4.0 / 1048576.0;
+    bool use_u16 = false, tuning = false;
+    if (const char *env = getenv("SD_QUANT_HOST_U16")) {
+        use_u16 = atoi(env) != 0;
+    } else {
+        bool alone = true;
+        if (const char *lw = getenv("LOCAL_WORLD_SIZE")) alone = atoi(lw) <= 1;
+        if (alone && cells_mb >= 256.0) {
+            tuning = true;
+            ++hp.tune_calls;
+            if (hp.ms_per_mb[0] <= 0) use_u16 = false;
+            else if (hp.ms_per_mb[1] <= 0) use_u16 = true;
+            else {
+                use_u16 = hp.ms_per_mb[1] < hp.ms_per_mb[0];
+                if (hp.tune_calls % 32 == 0) use_u16 = !use_u16;          // look at the other format again
+            }
+        }
+    }
     // row blocks of ~16 MB of int32 (8 MB on the link as uint16; 32 MB when everything crosses as
     // int32): 8 / 16 / 32 MB measured 33.4 / 32.8 / 33.3 ms with uint16, 38.6 / 36.4 / 36.3 ms
     // without.  Tuning knob for experiments: SD_QUANT_HOST_BLOCK_MB
@@ -333,8 +356,6 @@ int sd_quant_ps_host(int device, int64_t n_junctions, int32_t n_samples, const i
     int prev_dev = 0;
     SD_CHECK_CUDA(cudaGetDevice(&prev_dev));
     SD_CHECK_CUDA(cudaSetDevice(device));
-    HostPipe &hp = g_pipe[device];
-    std::lock_guard<std::mutex> pipe_lock(hp.mu);
 
     int32_t *d_counts = nullptr, *d_row_ptr = nullptr, *d_col = nullptr;
     uint16_t *d_stage = nullptr;
@@ -418,21 +439,14 @@ int sd_quant_ps_host(int device, int64_t n_junctions, int32_t n_samples, const i
     using clk = std::chrono::steady_clock;
     const auto t_begin = clk::now();
     double wait_narrow_ms = 0, wait_slot_ms = 0;
-    bool narrowing = use_u16;
     int64_t wide_blocks = 0;
     int64_t next_kernel = 0;
     for (int64_t b = 0; b < n_blocks; ++b) {
         const int64_t r0 = b * block_rows, r1 = std::min(J, r0 + block_rows);
         bool narrow_ok = false;
-        // guard: if the link keeps waiting for the narrowing threads (CPUs busy elsewhere), the
-        // remaining blocks cross as int32 straight from the caller's buffer
-        if (use_u16 && narrowing && b >= 8) {
-            const double elapsed = std::chrono::duration<double, std::milli>(clk::now() - t_begin).count();
-            if (wait_narrow_ms > 0.5 * elapsed) narrowing = false;
-        }
-        if (use_u16 && (narrowing || b < submitted)) {
+        if (use_u16) {
             // keep the narrowing up to kRingSlots - 1 blocks ahead of the copies
-            while (narrowing && submitted < n_blocks && submitted < b + kRingSlots) {
+            while (submitted < n_blocks && submitted < b + kRingSlots) {
                 const auto t0 = clk::now();
                 if (submitted >= kRingSlots) SD_TRY(cudaEventSynchronize(ev_copy[submitted - kRingSlots]));   // slot free again
                 wait_slot_ms += std::chrono::duration<double, std::milli>(clk::now() - t0).count();
@@ -495,6 +509,7 @@ int sd_quant_ps_host(int device, int64_t n_junctions, int32_t n_samples, const i
 #undef SD_TRY_RC
     const auto t_enqueued = clk::now();
     cleanup();
+    if (tuning) hp.ms_per_mb[use_u16 ? 1 : 0] = std::chrono::duration<double, std::milli>(clk::now() - t_begin).count() / cells_mb;
     if (debug)
         fprintf(stderr,
                 "[sd_quant_ps_host] %lld blocks of %lld rows, uint16 %s (%lld blocks sent as int32), %d workers: enqueue "
