@@ -19,6 +19,7 @@
 
 #include "sd_common.cuh"
 #include "sd_fisher_math.cuh"
+#include "sd_hostpipe.h"
 #include "sd_lgtable.h"
 
 namespace sd {
@@ -614,26 +615,28 @@ int sd_fisher_pairwise_host(int device, int64_t n_junctions, int32_t n_samples, 
     int prev_dev = 0;
     SD_CHECK_CUDA(cudaGetDevice(&prev_dev));
     SD_CHECK_CUDA(cudaSetDevice(device));
-    cudaStream_t s_k = nullptr, s_out = nullptr;
+    // streams and device memory come from the per-device context the host-buffer calls share: they
+    // live across calls, and the pool is private to the library (the process-wide default pool keeps
+    // its settings)
+    sd::HostLease lease;
+    if (int lrc = sd::host_lease(device, &lease)) { cudaSetDevice(prev_dev); return lrc; }
+    cudaStream_t s_k = lease.s_k, s_out = lease.s_out;
     int32_t *d_inc = nullptr, *d_pa = nullptr, *d_pb = nullptr;
     int64_t *d_exc = nullptr;
     double *d_p = nullptr;
     std::vector<cudaEvent_t> ev;
     int rc = SD_OK;
+    // every exit path: drain both streams before the buffers go back to the pool
     auto cleanup = [&]() {
-        for (auto e : ev) cudaEventDestroy(e);
-        if (s_out) cudaStreamSynchronize(s_out);
-        if (s_k) cudaStreamSynchronize(s_k);
-        if (s_k) {
-            if (d_inc) cudaFreeAsync(d_inc, s_k);
-            if (d_exc) cudaFreeAsync(d_exc, s_k);
-            if (d_pa) cudaFreeAsync(d_pa, s_k);
-            if (d_pb) cudaFreeAsync(d_pb, s_k);
-            if (d_p) cudaFreeAsync(d_p, s_k);
-            cudaStreamSynchronize(s_k);
-            cudaStreamDestroy(s_k);
-        }
-        if (s_out) cudaStreamDestroy(s_out);
+        cudaStreamSynchronize(s_out);
+        cudaStreamSynchronize(s_k);
+        for (auto e : ev) if (e) cudaEventDestroy(e);
+        if (d_inc) cudaFreeAsync(d_inc, s_k);
+        if (d_exc) cudaFreeAsync(d_exc, s_k);
+        if (d_pa) cudaFreeAsync(d_pa, s_k);
+        if (d_pb) cudaFreeAsync(d_pb, s_k);
+        if (d_p) cudaFreeAsync(d_p, s_k);
+        cudaStreamSynchronize(s_k);
         cudaSetDevice(prev_dev);
     };
 #define SD_TRY(expr)                                                                              \
@@ -646,24 +649,16 @@ int sd_fisher_pairwise_host(int device, int64_t n_junctions, int32_t n_samples, 
             return rc;                                                                            \
         }                                                                                         \
     } while (0)
-    SD_TRY(cudaStreamCreateWithFlags(&s_k, cudaStreamNonBlocking));
-    SD_TRY(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
     // p-value blocks of ~64 MB, double buffered (tuning knob for experiments: SD_FISHER_HOST_BLOCK_MB)
     int64_t block_mb = 64;
     if (const char *env = getenv("SD_FISHER_HOST_BLOCK_MB")) block_mb = std::max<int64_t>(1, atoll(env));
     int64_t block_rows = std::max<int64_t>(1, (block_mb << 20) / (n_pairs * 8));
     block_rows = std::min(block_rows, J);
-    {   // keep freed blocks in the default pool so repeated calls do not pay cudaMalloc again
-        cudaMemPool_t pool;
-        SD_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
-        uint64_t keep = ~0ull;
-        SD_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-    }
-    SD_TRY(cudaMallocAsync(&d_inc, (size_t)J * n_samples * 4, s_k));
-    SD_TRY(cudaMallocAsync(&d_exc, (size_t)J * n_samples * 8, s_k));
-    SD_TRY(cudaMallocAsync(&d_pa, (size_t)n_pairs * 4, s_k));
-    SD_TRY(cudaMallocAsync(&d_pb, (size_t)n_pairs * 4, s_k));
-    SD_TRY(cudaMallocAsync(&d_p, (size_t)2 * block_rows * n_pairs * 8, s_k));
+    SD_TRY(cudaMallocFromPoolAsync(&d_inc, (size_t)J * n_samples * 4, lease.pool, s_k));
+    SD_TRY(cudaMallocFromPoolAsync(&d_exc, (size_t)J * n_samples * 8, lease.pool, s_k));
+    SD_TRY(cudaMallocFromPoolAsync(&d_pa, (size_t)n_pairs * 4, lease.pool, s_k));
+    SD_TRY(cudaMallocFromPoolAsync(&d_pb, (size_t)n_pairs * 4, lease.pool, s_k));
+    SD_TRY(cudaMallocFromPoolAsync(&d_p, (size_t)2 * block_rows * n_pairs * 8, lease.pool, s_k));
     SD_TRY(cudaMemcpy2DAsync(d_inc, (size_t)n_samples * 4, inc, (size_t)ld_inc * 4, (size_t)n_samples * 4, (size_t)J,
                              cudaMemcpyHostToDevice, s_k));
     SD_TRY(cudaMemcpy2DAsync(d_exc, (size_t)n_samples * 8, exc, (size_t)ld_exc * 8, (size_t)n_samples * 8, (size_t)J,

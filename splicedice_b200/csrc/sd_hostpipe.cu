@@ -29,6 +29,7 @@
 #include <vector>
 
 #include "sd_common.cuh"
+#include "sd_hostpipe.h"
 #include "sd_quant.cuh"
 
 namespace sd {
@@ -255,6 +256,19 @@ struct NarrowJob {
 };
 
 }  // namespace
+
+// The per-device streams and the private pool for the other host-buffer entry point
+// (sd_fisher_pairwise_host): holds the device's lock until the lease is destroyed.
+int host_lease(int device, HostLease *lease)
+{
+    if (device < 0 || device >= kMaxDevices) return fail(SD_ERR_INVALID, "device ordinal %d out of range", device);
+    HostPipe &hp = g_pipe[device];
+    lease->lock = std::unique_lock<std::mutex>(hp.mu);
+    if (int rc = pipe_init(hp, device)) return rc;
+    lease->s_in = hp.s_in; lease->s_k = hp.s_k; lease->s_out = hp.s_out; lease->pool = hp.pool;
+    return SD_OK;
+}
+
 }  // namespace sd
 
 extern "C" {

@@ -154,7 +154,13 @@ def calculateIR(samples, coverageDirectory, counts, clusters, annotated, args, d
         have = counts[sample]
         for r, n in enumerate(all_names):
             if n in have:
-                inc[r, s] = int(have[n])
+                value = have[n]
+                if value != int(value):
+                    # the count matrix is integer on the device; the reference would carry the fraction
+                    # through its float arithmetic (ir_table.py:122-130) -- refuse rather than truncate
+                    raise ValueError(f"inclusion count {value!r} of {n} in {sample} is not an integer: the B200 path "
+                                     "takes the integer counts `quant` writes")
+                inc[r, s] = int(value)
             elif r < J:
                 raise KeyError(n)                # reference: prints and abandons the sample's file (:133-135)
     if (inc < 0).any() or (inc >= 2 ** 31).any():

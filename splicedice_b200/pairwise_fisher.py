@@ -68,7 +68,12 @@ def pairwise_pvalues(events, counts, clusters, device=0, correction="none", gpus
     pairs = sample_pairs(n_samples)
     if n_events == 0 or not pairs:
         return np.zeros((n_events, len(pairs)))
-    as_int = counts.astype(np.int64)                   # scipy truncates the table to int64 the same way
+    as_int = counts.astype(np.int64)
+    if not np.array_equal(as_int, counts):
+        # the reference sums the float rows first and lets scipy truncate the summed table
+        # (pairwise_fisher.py:158-165), so fractions would add up differently: refuse rather than guess
+        raise ValueError("inclusion counts must be integers (the table `quant` writes); fractional counts are "
+                         "not supported on the B200 path")
     if (as_int < 0).any():
         raise ValueError("All values in `table` must be nonnegative.")
     if (as_int >= 2 ** 31).any():

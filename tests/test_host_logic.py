@@ -372,3 +372,16 @@ def test_npz_writer_layout(tmp_path):
     assert sorted(z.files) == ["cols", "data", "rows"]
     assert z["cols"].tolist() == ["a", "b", "c"] and z["rows"].tolist() == ["chr1:5-90:+", "chr1:7-80:-"]
     assert z["data"].dtype == np.float32 and np.array_equal(z["data"], job.psi, equal_nan=True)
+
+
+def test_fractional_counts_are_refused_not_truncated():
+    """The reference would sum fractional rows in float and let scipy truncate the summed table
+    (pairwise_fisher.py:158-165); the integer device matrix cannot reproduce that, so such input is
+    refused loudly instead of being truncated cell by cell (no GPU is touched before the check)."""
+    from splicedice_b200 import pairwise_fisher
+    events = ["chr1:1-100:+", "chr1:50-200:+"]
+    clusters = {events[0]: [events[1]], events[1]: [events[0]]}
+    with pytest.raises(ValueError, match="integers"):
+        pairwise_fisher.pairwise_pvalues(events, np.array([[3.0, 4.6], [2.0, 5.0]]), clusters)
+    with pytest.raises(ValueError, match="nonnegative"):
+        pairwise_fisher.pairwise_pvalues(events, np.array([[3.0, -4.0], [2.0, 5.0]]), clusters)
