@@ -17,8 +17,13 @@ Modules
 -------
 oracle_np     numpy restatement of cluster build, exclusion sums, PS (f32/f64),
               IR/RSD and Benjamini-Hochberg.
+build_ref     pip-installs the UNMODIFIED reference into the git-ignored
+              ``oracle/_ref/`` (travels to the GPU box with the tree).
+ref_harness   drives that reference in memory; the timed CPU arm of bench.py
+              (one process, or closed row slabs over all host cores).
 ref_port      loop-for-loop port of the reference's Python hot loops (same data
-              structures, same cost profile) -- the CPU baseline that is timed.
+              structures, same cost profile) -- timed only when no reference
+              tree is installed.
 fisher_c      ctypes wrapper over ``fisher_oracle.c`` (binary128 restatement of
               scipy's two-sided ``fisher_exact``).
 """

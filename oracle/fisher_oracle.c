@@ -14,8 +14,9 @@
  * directly from binary128 lgamma and every tail is summed in binary128 the way
  * Boost's `hypergeometric_cdf_imp` does (start at the boundary term, walk away
  * from the mode with the term ratio), so the result is scipy's answer with the
- * ~1e-15 Boost rounding noise removed.  tests/test_fisher_oracle.py pins it to
- * scipy itself (and to mpmath exact sums) on the committed golden tables.
+ * ~1e-15 Boost rounding noise removed.  tests/test_oracle_golden.py pins it to
+ * scipy itself (and to mpmath exact sums) on the committed golden tables, and
+ * tests/test_reference_live.py to scipy run live.
  */
 #include <quadmath.h>
 #include <stdint.h>

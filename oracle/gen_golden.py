@@ -378,7 +378,8 @@ def main():
         json.dump({"generator": "oracle/gen_golden.py", "reference": "BrooksLabUCSC/splicedice @ /root/reference",
                    "numpy": np.__version__, "scipy": scipy.__version__,
                    "note": "BH correction in pairwise_{pairwise,all}.tsv comes from the harness stand-in "
-                           "for the absent statsmodels (oracle_np.bh_adjust)"}, f, indent=1)
+                           "for the absent statsmodels (oracle_np.bh_adjust, pinned to "
+                           "scipy.stats.false_discovery_control within 2 ulp: tests/test_bh_pin.py)"}, f, indent=1)
     print("golden fixtures written to", GOLD)
 
 

@@ -1,13 +1,14 @@
 """Loop-for-loop CPU port of the reference's hot loops (TEST ORACLE / CPU BASELINE).
 
-Test infrastructure -- see ``oracle/__init__.py``.  The reference is pure Python
-and cannot travel to the GPU box, so this port is what ``bench.py`` times as
-``cpu_baseline`` (``kind: "port"``) and what ``bench.py --impl reference`` runs.
-It keeps the reference's data structures (dict of tuples -> list of tuples, one
-numpy vector op per adjacency entry, one ``scipy.stats.fisher_exact`` call per
-table) so that it costs what the reference costs; ``tests/test_ref_port.py``
-checks it against the reference itself in the build container and against the
-committed golden vectors everywhere.
+Test infrastructure -- see ``oracle/__init__.py``.  ``bench.py`` times the
+UNMODIFIED reference (installed into ``oracle/_ref`` by ``oracle/build_ref.py``);
+this port is what it falls back to (``kind: "port"``) when no reference tree is
+installed.  It keeps the reference's data structures (dict of tuples -> list of
+tuples, one numpy vector op per adjacency entry, one ``scipy.stats.fisher_exact``
+call per table) so that it costs what the reference costs;
+``tests/test_reference_live.py`` checks it against the reference itself (bitwise
+PS, adjacency dict with list order, pairwise loop) wherever a reference tree
+exists.
 """
 from __future__ import annotations
 
