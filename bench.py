@@ -817,6 +817,28 @@ def main():
             del cols, work
             ops.bh_adjust(p_full, "pairwise", out=p_full)               # single-GPU correction of the whole matrix
             same_adj = torch.equal(adj.view(torch.int64), p_full[g0:g1].view(torch.int64))
+            # the same step with the exchange fused into the kernels: the Fisher kernel stores every p-value
+            # into the column owner's matrix over NVLink peer memory (sd_fisher_pairwise_scatter), BH in place,
+            # strided peer copies back -- no all-to-all, no packing (distributed.pairwise_fused)
+            fused = None
+            if world <= 16:
+                def nccl_path():
+                    ops.fisher_pairwise(inc_s, exc_s, d_pa, d_pb, out=p_slab, max_cell_bound=bound2)
+                    return sd_dist.bh_columns_sharded(p_slab, parts2, lambda c: ops.bh_adjust(c, "pairwise", out=c))
+
+                def fused_path():
+                    return sd_dist.pairwise_fused(inc_s, exc_s, d_pa, d_pb, parts2, bound2)
+
+                got_fused = fused_path()
+                same_fused = torch.equal(got_fused.view(torch.int64), p_full[g0:g1].view(torch.int64))
+                t_fused = max_over_ranks(timed_calls(fused_path, 5))
+                t_nccl = max_over_ranks(timed_calls(nccl_path, 5))
+                launches += 10
+                fused = {"what": "distributed.pairwise_fused: Fisher with peer-memory scatter stores + barrier + sd_bh_adjust in "
+                                 "place + strided peer copies back, against Fisher + NCCL all_to_all + sd_bh_adjust + all_to_all "
+                                 "(both: the whole per-slab pairwise step incl. Fisher)",
+                         "fused_whole_ms": t_fused, "nccl_whole_ms": t_nccl, "speedup": t_nccl / t_fused,
+                         "rows_bits_equal_one_gpu": all_true(same_fused)}
             slab_bytes = (g1 - g0) * P * 8
             sent = slab_bytes * (world - 1) / world
             collectives["pairwise_bh_exchange"] = {
@@ -826,7 +848,7 @@ def main():
                 "bytes_sent_per_gpu_each_way": int(sent),
                 "all_to_all_gbs_per_gpu_each_way": [sent / (x1 * 1e-3) / 1e9, sent / (x2 * 1e-3) / 1e9],
                 "nvlink5_per_direction_gbs": nvlink_gbs,
-                "adjusted_rows_bits_equal_one_gpu": all_true(same_adj),
+                "adjusted_rows_bits_equal_one_gpu": all_true(same_adj), "fused": fused,
                 "note": "exchange times include the column-block packing (contiguous copies) and torch.cat on arrival"}
             del adj, p_full, p_slab, inc2, exc2
             torch.cuda.empty_cache()

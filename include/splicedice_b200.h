@@ -180,6 +180,36 @@ int sd_fisher_pairwise_host(int device, int64_t n_junctions, int32_t n_samples,
                             const int64_t *exc, int64_t ld_exc,
                             int64_t n_pairs, const int32_t *pair_a, const int32_t *pair_b,
                             double *p_out, int64_t ld_p);
+/* Scatter form of the bounded call, for the multi-GPU pairwise path: the pairs are cut into n_dest
+ * contiguous column blocks [dest_col_begin[g], dest_col_begin[g + 1]) and the p-value of (row j,
+ * pair k) is stored straight into block owner g's matrix,
+ *   dest[g][(dest_row_offset + j) * dest_ld[g] + (k - dest_col_begin[g])].
+ * dest[g] are DEVICE pointers that may belong to other GPUs (peer memory, e.g. CUDA IPC mappings
+ * over NVLink): the row-slab -> column-block exchange that the per-pair Benjamini-Hochberg
+ * correction needs (pairwise_fisher.py:186-191 across GPUs) then happens inside the Fisher kernel's
+ * own stores instead of a separate all-to-all.  dest / dest_col_begin / dest_ld are HOST arrays
+ * (n_dest <= 16 entries, dest_col_begin has n_dest + 1).  Asynchronous on `stream`; the caller
+ * orders the peers (e.g. a barrier) before anybody reads the column blocks. */
+int sd_fisher_pairwise_scatter(int64_t n_junctions, int32_t n_samples,
+                               const int32_t *inc, int64_t ld_inc,
+                               const int64_t *exc, int64_t ld_exc,
+                               int64_t n_pairs, const int32_t *pair_a, const int32_t *pair_b,
+                               int32_t n_dest, double *const *dest, const int64_t *dest_col_begin,
+                               const int64_t *dest_ld, int64_t dest_row_offset,
+                               int64_t row_begin, int64_t row_end,
+                               int64_t max_cell_bound, void *stream);
+/* Peer-memory plumbing for that scatter (one process per GPU): allocate a device buffer and export
+ * it as a CUDA IPC handle (64 opaque bytes to hand to the other ranks, e.g. through
+ * torch.distributed.all_gather_object); map a peer's handle into this process (a device pointer
+ * valid on the caller's current device, NVLink peer access enabled by the mapping); strided
+ * device-to-device copy on the caller's stream (dst / src may be such mappings). */
+int sd_peer_alloc(size_t bytes, void **ptr, unsigned char *handle64);
+int sd_peer_free(void *ptr);
+int sd_peer_open(const unsigned char *handle64, void **ptr);
+int sd_peer_close(void *ptr);
+int sd_peer_copy2d(void *dst, size_t dst_pitch, const void *src, size_t src_pitch, size_t width_bytes, size_t height,
+                   void *stream);
+
 /* Element-wise form: p[i] for tables (a[i], b[i], c[i], d[i]) = [[a, b], [c, d]]. */
 int sd_fisher_tables(int64_t n_tables, const int64_t *a, const int64_t *b,
                      const int64_t *c, const int64_t *d, double *p_out, void *stream);

@@ -75,6 +75,7 @@ struct DeviceTable {
 };
 
 constexpr int kFisherThreads = 256;
+constexpr int kMaxDest = 16;
 
 struct FisherParams {
     int64_t n_junctions;
@@ -93,7 +94,29 @@ struct FisherParams {
     int32_t smem_entries;
     int64_t cell_bound;      // caller-promised (or measured) upper bound on inc + exc; entries outside [0, bound] give NaN
     bool binned;             // cost-binned kernel (every table total below 2^30)
+    // Scatter form (sd_fisher_pairwise_scatter): the pairs are cut into n_dest contiguous column
+    // blocks [dest_col[g], dest_col[g + 1]) and the p-value of (row j, pair k) goes straight to block
+    // owner g's matrix, dest[g][(dest_row0 + j) * dest_ld[g] + (k - dest_col[g])] -- the owners may be
+    // other GPUs (peer memory over NVLink), which turns the row-slab -> column-block exchange of the
+    // per-pair Benjamini-Hochberg correction into the kernel's own stores.
+    int32_t n_dest;          // 0: plain p_out
+    int32_t dest_col[kMaxDest + 1];
+    double *dest[kMaxDest];
+    int64_t dest_ld[kMaxDest];
+    int64_t dest_row0;
 };
+
+__device__ __forceinline__ void store_p(const FisherParams &p, int64_t j, int64_t k, double pv)
+{
+    if (p.n_dest == 0) {
+        __stcs(p.p_out + j * p.ld_p + k, pv);
+        return;
+    }
+    int g = 0;
+#pragma unroll 1
+    while (g + 1 < p.n_dest && k >= p.dest_col[g + 1]) ++g;
+    p.dest[g][(p.dest_row0 + j) * p.dest_ld[g] + (k - p.dest_col[g])] = pv;
+}
 
 __device__ __forceinline__ void stage_table(double2 *s_tab, const double2 *g_tab, int n)
 {
@@ -129,7 +152,7 @@ __global__ void __launch_bounds__(kFisherThreads, 3) fisher_pairwise_kernel(cons
                 pv = __longlong_as_double(0x7FF8000000000000ll);
             else
                 pv = fisher::two_sided<Int>(tab, (Int)a64, (Int)b64, (Int)c64, (Int)d64);
-            __stcs(p.p_out + j * p.ld_p + k, pv);
+            store_p(p, j, k, pv);
         }
         j += dj;
         t += dt;
@@ -295,7 +318,7 @@ __global__ void __launch_bounds__(kFisherThreads *kSub, 1) fisher_pairwise_binne
                     else
                         pv = fisher::two_sided<int32_t>(tab, a, b, c, d);
                 }
-                p.p_out[j * p.ld_p + k] = pv;
+                store_p(p, j, k, pv);
             }
         }
         group_sync(group);                      // s_perm / s_hist / the staged row are rebuilt by the next item
@@ -567,6 +590,39 @@ int sd_fisher_pairwise_bounded(int64_t n_junctions, int32_t n_samples, const int
     p.inc = inc; p.ld_inc = ld_inc; p.exc = exc; p.ld_exc = ld_exc;
     p.n_pairs = n_pairs; p.pair_a = pair_a; p.pair_b = pair_b;
     p.p_out = p_out; p.ld_p = ld_p; p.row_begin = row_begin; p.row_end = row_end;
+    return sd::launch_fisher_pairwise(p, (cudaStream_t)stream, max_cell_bound);
+}
+
+int sd_fisher_pairwise_scatter(int64_t n_junctions, int32_t n_samples, const int32_t *inc, int64_t ld_inc,
+                               const int64_t *exc, int64_t ld_exc, int64_t n_pairs, const int32_t *pair_a,
+                               const int32_t *pair_b, int32_t n_dest, double *const *dest, const int64_t *dest_col_begin,
+                               const int64_t *dest_ld, int64_t dest_row_offset, int64_t row_begin, int64_t row_end,
+                               int64_t max_cell_bound, void *stream)
+{
+    SD_REQUIRE(n_junctions >= 0 && n_samples >= 0 && n_pairs >= 0, "sd_fisher_pairwise_scatter: negative size");
+    SD_REQUIRE(row_begin >= 0 && row_begin <= row_end && row_end <= n_junctions,
+               "sd_fisher_pairwise_scatter: row range outside [0, n_junctions)");
+    SD_REQUIRE(max_cell_bound >= 0 && max_cell_bound < (int64_t(1) << 61), "sd_fisher_pairwise_scatter: bad bound");
+    SD_REQUIRE(n_dest >= 1 && n_dest <= sd::kMaxDest, "sd_fisher_pairwise_scatter: 1..%d destinations", sd::kMaxDest);
+    SD_REQUIRE(n_pairs < (int64_t(1) << 31), "sd_fisher_pairwise_scatter: too many pairs");
+    if (row_begin == row_end || n_pairs == 0) return SD_OK;
+    SD_REQUIRE(inc && exc && pair_a && pair_b && dest && dest_col_begin && dest_ld, "sd_fisher_pairwise_scatter: null pointer");
+    SD_REQUIRE(ld_inc >= n_samples && ld_exc >= n_samples, "sd_fisher_pairwise_scatter: ld too small");
+    SD_REQUIRE(dest_col_begin[0] == 0 && dest_col_begin[n_dest] == n_pairs,
+               "sd_fisher_pairwise_scatter: the column blocks must cover [0, n_pairs)");
+    sd::FisherParams p{};
+    p.n_junctions = n_junctions; p.n_samples = n_samples;
+    p.inc = inc; p.ld_inc = ld_inc; p.exc = exc; p.ld_exc = ld_exc;
+    p.n_pairs = n_pairs; p.pair_a = pair_a; p.pair_b = pair_b;
+    p.p_out = nullptr; p.ld_p = 0; p.row_begin = row_begin; p.row_end = row_end;
+    p.n_dest = n_dest; p.dest_row0 = dest_row_offset;
+    for (int g = 0; g < n_dest; ++g) {
+        const int64_t width = dest_col_begin[g + 1] - dest_col_begin[g];
+        SD_REQUIRE(width >= 0 && (width == 0 || (dest[g] && dest_ld[g] >= width)),
+                   "sd_fisher_pairwise_scatter: destination %d: null pointer or ld below its %lld columns", g, (long long)width);
+        p.dest[g] = dest[g]; p.dest_ld[g] = dest_ld[g]; p.dest_col[g] = (int32_t)dest_col_begin[g];
+    }
+    p.dest_col[n_dest] = (int32_t)n_pairs;
     return sd::launch_fisher_pairwise(p, (cudaStream_t)stream, max_cell_bound);
 }
 

@@ -188,6 +188,126 @@ def bh_columns_sharded(p_local, parts, adjust_fn):
     return columns_to_rows(adjust_fn(cols), parts, n_cols)
 
 
+# ---- the same exchange fused into the kernels: peer memory over NVLink -------------------------
+# Instead of "Fisher -> all-to-all -> BH -> all-to-all", every rank's Fisher kernel stores each
+# p-value straight into the column-block owner's matrix (sd_fisher_pairwise_scatter writes through
+# CUDA IPC mappings of the peers' buffers), one barrier orders the GPUs, every rank adjusts its
+# column block in place, and the adjusted blocks go back to the row owners as strided peer copies.
+# No packing, no staging buffers, no NCCL on the data path (NCCL carries the barriers and the
+# one-off exchange of the IPC handles).
+_PEER_CACHE = {}
+
+
+class _RawCuda:
+    """A raw device allocation as something torch.as_tensor can alias (__cuda_array_interface__)."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(int(x) for x in shape), "typestr": "<f8", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class PeerMatrix:
+    """One float64 matrix per rank, every rank able to address all of them: this rank's own
+    allocation (sd_peer_alloc; ``own`` is a torch tensor aliasing it) and CUDA IPC mappings of the
+    others' (sd_peer_open).  ``ptrs[g]`` / ``lds[g]`` / ``shapes[g]``: rank g's base pointer, leading
+    dimension in elements and shape.  Shapes may differ by rank."""
+
+    def __init__(self, shape, dev):
+        import ctypes
+        from . import native
+        rank, world = _world()
+        self.dev = dev
+        self.shape = tuple(int(x) for x in shape)
+        nbytes = max(1, self.shape[0] * self.shape[1] * 8)
+        ptr = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * 64)()
+        with torch.cuda.device(dev):
+            native.call("sd_peer_alloc", nbytes, ctypes.byref(ptr), handle)
+        self._own_ptr = ptr.value
+        self.own = torch.as_tensor(_RawCuda(ptr.value, self.shape), device=dev) if self.shape[0] * self.shape[1] else \
+            torch.empty(self.shape, dtype=torch.float64, device=dev)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (bytes(handle), self.shape))
+        self.ptrs, self.lds, self.shapes, self._opened = [], [], [], []
+        for g, (h, shp) in enumerate(gathered):
+            self.shapes.append(shp)
+            self.lds.append(shp[1])
+            if g == rank:
+                self.ptrs.append(self._own_ptr)
+                continue
+            peer = ctypes.c_void_p()
+            buf = (ctypes.c_ubyte * 64).from_buffer_copy(h)
+            with torch.cuda.device(dev):
+                native.call("sd_peer_open", buf, ctypes.byref(peer))
+            self.ptrs.append(peer.value)
+            self._opened.append(peer.value)
+
+    def close(self):
+        from . import native
+        torch.cuda.synchronize(self.dev)
+        if dist.is_initialized():
+            dist.barrier()                          # nobody is still reading this rank's buffer
+        with torch.cuda.device(self.dev):
+            for p in self._opened:
+                native.call("sd_peer_close", p)
+            self._opened = []
+            if self._own_ptr:
+                self.own = None
+                native.call("sd_peer_free", self._own_ptr)
+                self._own_ptr = None
+
+
+def _peer_matrix(tag, shape, dev):
+    hit = _PEER_CACHE.get(tag)
+    if hit is not None and hit.shape == tuple(shape) and hit.dev == dev:
+        return hit
+    if hit is not None:
+        hit.close()
+    _PEER_CACHE[tag] = PeerMatrix(shape, dev)
+    return _PEER_CACHE[tag]
+
+
+def release_peer_buffers():
+    """Unmap and free every cached peer buffer (collective: every rank calls it)."""
+    for tag in list(_PEER_CACHE):
+        _PEER_CACHE.pop(tag).close()
+
+
+def pairwise_fused(inc, exc, pair_a, pair_b, parts, bound, adjust=True):
+    """Fisher + per-pair Benjamini-Hochberg of a row-sharded problem with the exchange fused into the
+    kernels' stores.  inc / exc: this rank's slab (CUDA); parts: every rank's (row_begin, row_end).
+    Returns float64 CUDA [rows_r, P] (a cached peer buffer: copy it if it must outlive the next call)."""
+    import ctypes
+    from . import native, ops
+    rank, world = _world()
+    dev = inc.device
+    P = int(len(pair_a))
+    J = parts[-1][1]
+    r0, r1 = parts[rank]
+    blocks = column_blocks(P, world)
+    c0, c1 = blocks[rank]
+    cols = _peer_matrix(("cols", J, P, world), (J, c1 - c0), dev)
+    rows = _peer_matrix(("rows", J, P, world), (r1 - r0, P), dev)
+    pa, pb = ops._i32(pair_a, dev), ops._i32(pair_b, dev)
+    n = world
+    ptrs = (ctypes.c_void_p * n)(*cols.ptrs)
+    cuts = (ctypes.c_int64 * (n + 1))(*([b[0] for b in blocks] + [P]))
+    lds = (ctypes.c_int64 * n)(*cols.lds)
+    with torch.cuda.device(dev):
+        native.call("sd_fisher_pairwise_scatter", inc.shape[0], inc.shape[1], native.ptr(inc), inc.stride(0),
+                    native.ptr(exc), exc.stride(0), P, native.ptr(pa), native.ptr(pb), n, ptrs, cuts, lds, r0, 0,
+                    inc.shape[0], int(bound), native.stream_ptr())
+        dist.barrier()                               # every GPU's stores into this rank's column block are done
+        if adjust and c1 > c0:
+            ops.bh_adjust(cols.own, "pairwise", out=cols.own)
+        for g, (a, b) in enumerate(parts):           # adjusted block -> the row owners: strided peer copies
+            if b > a and c1 > c0:
+                native.call("sd_peer_copy2d", rows.ptrs[g] + c0 * 8, rows.lds[g] * 8, cols.own.data_ptr() + a * (c1 - c0) * 8,
+                            (c1 - c0) * 8, (c1 - c0) * 8, b - a, native.stream_ptr())
+        dist.barrier()                               # every rank's rows are complete
+    return rows.own
+
+
 def pairwise_sharded(counts_host, row_ptr, col_idx, correction="pairwise", device=None):
     """``splicedice pairwise`` arithmetic over the ranks' GPUs: exclusion sums + Fisher on this
     rank's row slab, then the correction.  counts_host: integer [J, S] on every rank (each uploads
@@ -212,6 +332,9 @@ def pairwise_sharded(counts_host, row_ptr, col_idx, correction="pairwise", devic
     exc = ops.quant_ps(inc, rp, ci, want_f32=False, want_exc=True)["exc"]
     pa, pb = ops.all_pairs(S)
     bound = int(slab.max(initial=0)) * (1 + int(np.diff(rp).max(initial=0)))
+    if correction == "pairwise" and world > 1 and dist.get_backend() == "nccl" and world <= 16 and len(pa) >= world:
+        # the exchange rides on the kernels' own stores (peer memory); see pairwise_fused
+        return pairwise_fused(inc, exc, pa, pb, parts, bound).clone(), (r0, r1)
     p = ops.fisher_pairwise(inc, exc, pa, pb, max_cell_bound=bound)
     if correction == "pairwise":
         p = bh_columns_sharded(p, parts, lambda cols: ops.bh_adjust(cols, "pairwise", out=cols))
