@@ -209,6 +209,11 @@ int sd_peer_open(const unsigned char *handle64, void **ptr);
 int sd_peer_close(void *ptr);
 int sd_peer_copy2d(void *dst, size_t dst_pitch, const void *src, size_t src_pitch, size_t width_bytes, size_t height,
                    void *stream);
+/* The way back: rows [row_begin[g], row_begin[g + 1]) of the dense DEVICE matrix src[n_rows, width]
+ * go to dest[g] (row owner g's matrix, possibly peer memory) at rows 0.., columns dest_col0.. --
+ * one kernel, 256-byte contiguous stores.  dest / row_begin / dest_ld are HOST arrays. */
+int sd_peer_scatter_rows(const double *src, int64_t n_rows, int64_t width, int32_t n_dest, double *const *dest,
+                         const int64_t *row_begin, const int64_t *dest_ld, int64_t dest_col0, void *stream);
 
 /* Element-wise form: p[i] for tables (a[i], b[i], c[i], d[i]) = [[a, b], [c, d]]. */
 int sd_fisher_tables(int64_t n_tables, const int64_t *a, const int64_t *b,

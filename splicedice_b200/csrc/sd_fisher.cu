@@ -100,6 +100,8 @@ struct FisherParams {
     // other GPUs (peer memory over NVLink), which turns the row-slab -> column-block exchange of the
     // per-pair Benjamini-Hochberg correction into the kernel's own stores.
     int32_t n_dest;          // 0: plain p_out
+    int32_t stage_out;       // binned kernel: byte offset (from the dynamic shared memory base) of kSub x kBinChunk doubles
+                             // in which a chunk's p-values are collected and then stored in pair order; 0 = store directly
     int32_t dest_col[kMaxDest + 1];
     double *dest[kMaxDest];
     int64_t dest_ld[kMaxDest];
@@ -228,6 +230,11 @@ __global__ void __launch_bounds__(kFisherThreads *kSub, 1) fisher_pairwise_binne
     fisher::SampleTerms *s_pre =
         reinterpret_cast<fisher::SampleTerms *>(reinterpret_cast<GroupBins *>(s_tab + p.smem_entries) + kSub) +
         (size_t)group * p.n_samples;
+    // scatter form: a chunk's p-values are collected here and written out in pair order, so that a warp
+    // stores 256 contiguous bytes per destination instead of 32 scattered doubles (which would cross
+    // NVLink as 32 separate 8-byte writes)
+    double *s_out = p.stage_out ? reinterpret_cast<double *>(reinterpret_cast<char *>(s_tab) + p.stage_out) + (size_t)group * kBinChunk
+                                : nullptr;
     uint16_t *s_perm = bins.perm, *s_rank = bins.rank;
     uint8_t *s_key = bins.key;
     int *s_hist = bins.hist, *s_base = bins.base, *s_next = &bins.next;
@@ -318,8 +325,13 @@ __global__ void __launch_bounds__(kFisherThreads *kSub, 1) fisher_pairwise_binne
                     else
                         pv = fisher::two_sided<int32_t>(tab, a, b, c, d);
                 }
-                store_p(p, j, k, pv);
+                if (s_out) s_out[s_perm[slot]] = pv;
+                else store_p(p, j, k, pv);
             }
+        }
+        if (s_out) {
+            group_sync(group);
+            for (int q = tid; q < cnt; q += kFisherThreads) store_p(p, j, k0 + q, s_out[q]);
         }
         group_sync(group);                      // s_perm / s_hist / the staged row are rebuilt by the next item
     }
@@ -476,12 +488,18 @@ struct PairwiseLauncher {
         const bool use_pre = kStaged && base + pre <= kMaxSmem && !getenv("SD_FISHER_NO_PRE");
         auto kernel = use_pre ? fisher_pairwise_binned_kernel<kMode, kSub, kStaged, kStaged>
                               : fisher_pairwise_binned_kernel<kMode, kSub, kStaged, false>;
-        const size_t smem = base + (use_pre ? pre : 0);
+        size_t smem = base + (use_pre ? pre : 0);
+        FisherParams q = p;
+        const size_t stage = (size_t)kSub * kBinChunk * sizeof(double);
+        if (p.n_dest > 0 && smem + stage <= kMaxSmem) {          // scatter form with room to collect a chunk's outputs
+            q.stage_out = (int32_t)smem;
+            smem += stage;
+        }
         SD_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
         const int64_t items = (p.row_end - p.row_begin) * ((p.n_pairs + kBinChunk - 1) / kBinChunk);
         int grid = fisher_grid((const void *)kernel, smem, kFisherThreads * kSub);
         grid = (int)std::min<int64_t>(grid, (items + kSub - 1) / kSub);
-        kernel<<<grid, kFisherThreads * kSub, smem, stream>>>(p);
+        kernel<<<grid, kFisherThreads * kSub, smem, stream>>>(q);
         return check_launch("fisher_pairwise_binned_kernel");
     }
     static int run(const FisherParams &p, cudaStream_t stream)
