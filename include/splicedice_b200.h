@@ -201,14 +201,11 @@ int sd_fisher_pairwise_scatter(int64_t n_junctions, int32_t n_samples,
 /* Peer-memory plumbing for that scatter (one process per GPU): allocate a device buffer and export
  * it as a CUDA IPC handle (64 opaque bytes to hand to the other ranks, e.g. through
  * torch.distributed.all_gather_object); map a peer's handle into this process (a device pointer
- * valid on the caller's current device, NVLink peer access enabled by the mapping); strided
- * device-to-device copy on the caller's stream (dst / src may be such mappings). */
+ * valid on the caller's current device, NVLink peer access enabled by the mapping). */
 int sd_peer_alloc(size_t bytes, void **ptr, unsigned char *handle64);
 int sd_peer_free(void *ptr);
 int sd_peer_open(const unsigned char *handle64, void **ptr);
 int sd_peer_close(void *ptr);
-int sd_peer_copy2d(void *dst, size_t dst_pitch, const void *src, size_t src_pitch, size_t width_bytes, size_t height,
-                   void *stream);
 /* The way back: rows [row_begin[g], row_begin[g + 1]) of the dense DEVICE matrix src[n_rows, width]
  * go to dest[g] (row owner g's matrix, possibly peer memory) at rows 0.., columns dest_col0.. --
  * one kernel, 256-byte contiguous stores.  dest / row_begin / dest_ld are HOST arrays. */

@@ -7,7 +7,7 @@
 // points allocate such a buffer, export it as a CUDA IPC handle (64 opaque bytes the ranks exchange
 // through torch.distributed), and map a peer's handle into the calling process: the mapping is a
 // device pointer valid on the caller's current device, backed by NVLink peer access.  The adjusted
-// column blocks travel back with sd_peer_copy2d (a strided copy on the caller's stream).
+// column blocks travel back with sd_peer_scatter_rows (one kernel of peer stores).
 #include <string.h>
 
 #include "sd_common.cuh"
@@ -102,15 +102,6 @@ int sd_peer_open(const unsigned char *handle64, void **ptr)
 int sd_peer_close(void *ptr)
 {
     if (ptr) SD_CHECK_CUDA(cudaIpcCloseMemHandle(ptr));
-    return SD_OK;
-}
-
-int sd_peer_copy2d(void *dst, size_t dst_pitch, const void *src, size_t src_pitch, size_t width_bytes, size_t height,
-                   void *stream)
-{
-    if (width_bytes == 0 || height == 0) return SD_OK;
-    SD_REQUIRE(dst && src && dst_pitch >= width_bytes && src_pitch >= width_bytes, "sd_peer_copy2d: bad arguments");
-    SD_CHECK_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width_bytes, height, cudaMemcpyDefault, (cudaStream_t)stream));
     return SD_OK;
 }
 

@@ -62,7 +62,6 @@ _SIGNATURES = {
     "sd_peer_free": (c_int, [_P]),
     "sd_peer_open": (c_int, [_P, POINTER(c_void_p)]),
     "sd_peer_close": (c_int, [_P]),
-    "sd_peer_copy2d": (c_int, [_P, c_size_t, _P, c_size_t, c_size_t, c_size_t, _P]),
     "sd_peer_scatter_rows": (c_int, [_P, c_int64, c_int64, c_int32, _P, _P, _P, c_int64, _P]),
     "sd_fisher_tables": (c_int, [c_int64, _P, _P, _P, _P, _P, _P]),
     "sd_fisher_pairwise_host": (c_int, [c_int, c_int64, c_int32, _P, c_int64, _P, c_int64,
