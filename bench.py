@@ -550,7 +550,7 @@ def main():
         h_counts.copy_(counts)
         h_ps = torch.empty((Jr, S), dtype=torch.float32).pin_memory()
         n_e2e = max(3, min(args.steps, 7))
-        for _ in range(3):       # warm-up: allocations, pool; the library times one call per link format and keeps the faster
+        for _ in range(5):       # warm-up: allocations, pool; the library times two calls per link format and keeps the faster
             ops.quant_ps_host(h_counts, rp, ci, out=h_ps, device=local_rank)
         per_call = []
         for _ in range(n_e2e):
@@ -683,14 +683,13 @@ def main():
         # host-buffer API for the e2e figure (p-values come back to the host)
         if not args.no_e2e:
             inc_h_all = torch.empty(inc.shape, dtype=torch.int32).pin_memory(); inc_h_all.copy_(inc)
-            exc_h_all = torch.empty(exc.shape, dtype=torch.int64).pin_memory(); exc_h_all.copy_(exc)
             out_h = torch.empty((Jfr, P), dtype=torch.float64).pin_memory()
-            ops.fisher_pairwise_host(inc_h_all, exc_h_all, pa, pb, out=out_h, device=local_rank)
+            ops.pairwise_host(inc_h_all, frp, fci, pa, pb, out=out_h, device=local_rank)
             per_call = []
             for _ in range(3):
                 barrier()
                 t0 = time.perf_counter()
-                ops.fisher_pairwise_host(inc_h_all, exc_h_all, pa, pb, out=out_h, device=local_rank)
+                ops.pairwise_host(inc_h_all, frp, fci, pa, pb, out=out_h, device=local_rank)
                 per_call.append(max_over_ranks(time.perf_counter() - t0))
             dt = float(np.mean(per_call))
             if not torch.equal(out_h.view(torch.int64), pout.cpu().view(torch.int64)):
@@ -699,11 +698,13 @@ def main():
             if e2e is not None:
                 d2h_floor = out_h.numel() * 8 * world / (e2e["fabric"]["d2h_gbs"] * 1e9) * 1e3
             fisher["e2e"] = {"value": tests_total / dt, "unit": "tests/s", "ms_per_step": dt * 1e3,
-                             "h2d_bytes_per_step": int(inc_h_all.numel() * 4 + exc_h_all.numel() * 8),
+                             "api": "sd_pairwise_host (pinned host inclusion counts + cluster CSR -> pinned host p-values; "
+                                    "exclusion counts summed on the device)",
+                             "h2d_bytes_per_step": int(inc_h_all.numel() * 4 + frp.nbytes + fci.nbytes),
                              "d2h_bytes_per_step": int(out_h.numel() * 8),
                              "d2h_alone_ms_at_fabric_rate": d2h_floor,
                              "frac_of_fabric": (d2h_floor / (dt * 1e3)) if d2h_floor else None}
-            del out_h, inc_h_all, exc_h_all
+            del out_h, inc_h_all
         del pout, inc, exc
         torch.cuda.empty_cache()
 

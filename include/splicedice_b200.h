@@ -180,6 +180,16 @@ int sd_fisher_pairwise_host(int device, int64_t n_junctions, int32_t n_samples,
                             const int64_t *exc, int64_t ld_exc,
                             int64_t n_pairs, const int32_t *pair_a, const int32_t *pair_b,
                             double *p_out, int64_t ld_p);
+/* The whole hot loop of pairwise_fisher.run_with (pairwise_fisher.py:154-180) for HOST buffers:
+ * inclusion counts and the cluster CSR (np.isin set semantics are the caller's: one entry per
+ * distinct partner) in, p-values out.  The exclusion counts are summed on the device (the kernel of
+ * sd_quant_ps), so 4 bytes per cell cross the link instead of 12, then the same pipeline as
+ * sd_fisher_pairwise_host runs.  Every pointer is a HOST pointer. */
+int sd_pairwise_host(int device, int64_t n_junctions, int32_t n_samples,
+                     const int32_t *inc, int64_t ld_inc,
+                     const int32_t *row_ptr, const int32_t *col_idx,
+                     int64_t n_pairs, const int32_t *pair_a, const int32_t *pair_b,
+                     double *p_out, int64_t ld_p);
 /* Scatter form of the bounded call, for the multi-GPU pairwise path: the pairs are cut into n_dest
  * contiguous column blocks [dest_col_begin[g], dest_col_begin[g + 1]) and the p-value of (row j,
  * pair k) is stored straight into block owner g's matrix,

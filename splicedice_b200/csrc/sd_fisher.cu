@@ -21,6 +21,7 @@
 #include "sd_fisher_math.cuh"
 #include "sd_hostpipe.h"
 #include "sd_lgtable.h"
+#include "sd_quant.cuh"
 
 namespace sd {
 
@@ -670,32 +671,40 @@ int sd_fisher_tables(int64_t n_tables, const int64_t *a, const int64_t *b, const
                                             entries, smem_entries, stream);
 }
 
-// Host-buffer form: inc / exc / pairs / p_out are HOST pointers.  Row blocks of p-values are
-// computed on one stream and copied back on another, so the 8 B/test of D2H traffic overlaps
-// the FP64 work.
-int sd_fisher_pairwise_host(int device, int64_t n_junctions, int32_t n_samples, const int32_t *inc,
-                            int64_t ld_inc, const int64_t *exc, int64_t ld_exc, int64_t n_pairs,
-                            const int32_t *pair_a, const int32_t *pair_b, double *p_out, int64_t ld_p)
+}  // extern "C"
+
+namespace sd {
+
+// Host-buffer pipeline shared by sd_fisher_pairwise_host (exclusion counts given) and sd_pairwise_host
+// (exclusion counts computed on the device from the inclusion counts and the cluster CSR): row blocks
+// of p-values are computed on one stream and copied back on another, so the 8 B/test of D2H traffic
+// -- the bound: 3.2 GB against 19 ms of FP64 work at 200,000 x 2,016 -- overlaps the kernels.  The
+// first blocks are small so that the copy-back stream starts within a fraction of a millisecond.
+static int pairwise_host_impl(const char *who, int device, int64_t J, int32_t n_samples, const int32_t *inc, int64_t ld_inc,
+                              const int64_t *exc, int64_t ld_exc, const int32_t *row_ptr, const int32_t *col_idx,
+                              int64_t n_pairs, const int32_t *pair_a, const int32_t *pair_b, double *p_out, int64_t ld_p)
 {
-    SD_REQUIRE(n_junctions >= 0 && n_samples >= 0 && n_pairs >= 0, "sd_fisher_pairwise_host: negative size");
-    if (n_junctions == 0 || n_pairs == 0) return SD_OK;
-    SD_REQUIRE(inc && exc && pair_a && pair_b && p_out, "sd_fisher_pairwise_host: null pointer");
-    SD_REQUIRE(ld_inc >= n_samples && ld_exc >= n_samples && ld_p >= n_pairs,
-               "sd_fisher_pairwise_host: ld too small");
     for (int64_t k = 0; k < n_pairs; ++k)
-        SD_REQUIRE(pair_a[k] >= 0 && pair_a[k] < n_samples && pair_b[k] >= 0 && pair_b[k] < n_samples,
-                   "sd_fisher_pairwise_host: pair %lld out of range", (long long)k);
-    const int64_t J = n_junctions;
+        if (!(pair_a[k] >= 0 && pair_a[k] < n_samples && pair_b[k] >= 0 && pair_b[k] < n_samples))
+            return fail(SD_ERR_INVALID, "%s: pair %lld out of range", who, (long long)k);
+    int64_t nnz = 0;
+    if (!exc) {
+        nnz = row_ptr[J];
+        if (nnz < 0 || (nnz > 0 && !col_idx)) return fail(SD_ERR_INVALID, "%s: bad CSR", who);
+        for (int64_t k = 0; k < nnz; ++k)
+            if (col_idx[k] < 0 || col_idx[k] >= J)
+                return fail(SD_ERR_INVALID, "%s: col_idx[%lld] = %d out of range", who, (long long)k, col_idx[k]);
+    }
     int prev_dev = 0;
     SD_CHECK_CUDA(cudaGetDevice(&prev_dev));
     SD_CHECK_CUDA(cudaSetDevice(device));
     // streams and device memory come from the per-device context the host-buffer calls share: they
     // live across calls, and the pool is private to the library (the process-wide default pool keeps
     // its settings)
-    sd::HostLease lease;
-    if (int lrc = sd::host_lease(device, &lease)) { cudaSetDevice(prev_dev); return lrc; }
+    HostLease lease;
+    if (int lrc = host_lease(device, &lease)) { cudaSetDevice(prev_dev); return lrc; }
     cudaStream_t s_k = lease.s_k, s_out = lease.s_out;
-    int32_t *d_inc = nullptr, *d_pa = nullptr, *d_pb = nullptr;
+    int32_t *d_inc = nullptr, *d_pa = nullptr, *d_pb = nullptr, *d_rp = nullptr, *d_ci = nullptr;
     int64_t *d_exc = nullptr;
     double *d_p = nullptr;
     std::vector<cudaEvent_t> ev;
@@ -705,11 +714,8 @@ int sd_fisher_pairwise_host(int device, int64_t n_junctions, int32_t n_samples, 
         cudaStreamSynchronize(s_out);
         cudaStreamSynchronize(s_k);
         for (auto e : ev) if (e) cudaEventDestroy(e);
-        if (d_inc) cudaFreeAsync(d_inc, s_k);
-        if (d_exc) cudaFreeAsync(d_exc, s_k);
-        if (d_pa) cudaFreeAsync(d_pa, s_k);
-        if (d_pb) cudaFreeAsync(d_pb, s_k);
-        if (d_p) cudaFreeAsync(d_p, s_k);
+        for (void *q : {(void *)d_inc, (void *)d_exc, (void *)d_pa, (void *)d_pb, (void *)d_p, (void *)d_rp, (void *)d_ci})
+            if (q) cudaFreeAsync(q, s_k);
         cudaStreamSynchronize(s_k);
         cudaSetDevice(prev_dev);
     };
@@ -723,43 +729,64 @@ int sd_fisher_pairwise_host(int device, int64_t n_junctions, int32_t n_samples, 
             return rc;                                                                            \
         }                                                                                         \
     } while (0)
-    // p-value blocks of ~64 MB, double buffered (tuning knob for experiments: SD_FISHER_HOST_BLOCK_MB)
+    // p-value blocks of ~64 MB, double buffered, after a ramp of 2, 8 and 32 MB
+    // (tuning knob for experiments: SD_FISHER_HOST_BLOCK_MB)
     int64_t block_mb = 64;
     if (const char *env = getenv("SD_FISHER_HOST_BLOCK_MB")) block_mb = std::max<int64_t>(1, atoll(env));
-    int64_t block_rows = std::max<int64_t>(1, (block_mb << 20) / (n_pairs * 8));
-    block_rows = std::min(block_rows, J);
-    SD_TRY(cudaMallocFromPoolAsync(&d_inc, (size_t)J * n_samples * 4, lease.pool, s_k));
-    SD_TRY(cudaMallocFromPoolAsync(&d_exc, (size_t)J * n_samples * 8, lease.pool, s_k));
+    const int64_t full_rows = std::min<int64_t>(J, std::max<int64_t>(1, (block_mb << 20) / (n_pairs * 8)));
+    std::vector<int64_t> cut{0};
+    for (int64_t rows = std::max<int64_t>(1, full_rows / 32); cut.back() < J; rows = std::min(full_rows, rows * 4))
+        cut.push_back(std::min(J, cut.back() + rows));
+    const int64_t n_blocks = (int64_t)cut.size() - 1;
+    const int64_t ldd = (n_samples + 3) & ~(int64_t)3;           // device leading dimension of the count matrices
+    SD_TRY(cudaMallocFromPoolAsync(&d_inc, (size_t)J * ldd * 4, lease.pool, s_k));
+    SD_TRY(cudaMallocFromPoolAsync(&d_exc, (size_t)J * ldd * 8, lease.pool, s_k));
     SD_TRY(cudaMallocFromPoolAsync(&d_pa, (size_t)n_pairs * 4, lease.pool, s_k));
     SD_TRY(cudaMallocFromPoolAsync(&d_pb, (size_t)n_pairs * 4, lease.pool, s_k));
-    SD_TRY(cudaMallocFromPoolAsync(&d_p, (size_t)2 * block_rows * n_pairs * 8, lease.pool, s_k));
-    SD_TRY(cudaMemcpy2DAsync(d_inc, (size_t)n_samples * 4, inc, (size_t)ld_inc * 4, (size_t)n_samples * 4, (size_t)J,
+    SD_TRY(cudaMallocFromPoolAsync(&d_p, (size_t)2 * full_rows * n_pairs * 8, lease.pool, s_k));
+    if (ldd != n_samples) SD_TRY(cudaMemsetAsync(d_inc, 0, (size_t)J * ldd * 4, s_k));
+    SD_TRY(cudaMemcpy2DAsync(d_inc, (size_t)ldd * 4, inc, (size_t)ld_inc * 4, (size_t)n_samples * 4, (size_t)J,
                              cudaMemcpyHostToDevice, s_k));
-    SD_TRY(cudaMemcpy2DAsync(d_exc, (size_t)n_samples * 8, exc, (size_t)ld_exc * 8, (size_t)n_samples * 8, (size_t)J,
-                             cudaMemcpyHostToDevice, s_k));
+    if (exc) {
+        SD_TRY(cudaMemcpy2DAsync(d_exc, (size_t)ldd * 8, exc, (size_t)ld_exc * 8, (size_t)n_samples * 8, (size_t)J,
+                                 cudaMemcpyHostToDevice, s_k));
+    } else {
+        // exclusion counts on the device: 4 B per cell cross the link instead of 12
+        SD_TRY(cudaMallocFromPoolAsync(&d_rp, (size_t)(J + 1) * 4, lease.pool, s_k));
+        SD_TRY(cudaMallocFromPoolAsync(&d_ci, (size_t)std::max<int64_t>(nnz, 1) * 4, lease.pool, s_k));
+        SD_TRY(cudaMemcpyAsync(d_rp, row_ptr, (size_t)(J + 1) * 4, cudaMemcpyHostToDevice, s_k));
+        if (nnz) SD_TRY(cudaMemcpyAsync(d_ci, col_idx, (size_t)nnz * 4, cudaMemcpyHostToDevice, s_k));
+        QuantParams q{};
+        q.n_junctions = J; q.n_samples = n_samples;
+        q.counts = d_inc; q.ld_counts = ldd;
+        q.row_ptr = d_rp; q.col_idx = d_ci;
+        q.exc = d_exc; q.ld_exc = ldd;
+        q.row_begin = 0; q.row_end = J;
+        rc = launch_quant(q, SD_QUANT_AUTO, s_k);
+        if (rc != SD_OK) { cleanup(); return rc; }
+    }
     SD_TRY(cudaMemcpyAsync(d_pa, pair_a, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, s_k));
     SD_TRY(cudaMemcpyAsync(d_pb, pair_b, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, s_k));
-    const int64_t n_blocks = (J + block_rows - 1) / block_rows;
     int64_t max_cell = 0;
     {
-        sd::FisherParams all{};
-        all.n_samples = n_samples; all.inc = d_inc; all.ld_inc = n_samples; all.exc = d_exc; all.ld_exc = n_samples;
+        FisherParams all{};
+        all.n_samples = n_samples; all.inc = d_inc; all.ld_inc = ldd; all.exc = d_exc; all.ld_exc = ldd;
         all.row_begin = 0; all.row_end = J;
-        rc = sd::fisher_max_cell(all, s_k, &max_cell);
+        rc = fisher_max_cell(all, s_k, &max_cell);
         if (rc != SD_OK) { cleanup(); return rc; }
     }
     ev.resize((size_t)2 * n_blocks, nullptr);
     for (auto &e : ev) SD_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (int64_t b = 0; b < n_blocks; ++b) {
-        const int64_t r0 = b * block_rows, r1 = std::min(J, r0 + block_rows);
-        double *buf = d_p + (b & 1) * block_rows * n_pairs;
+        const int64_t r0 = cut[b], r1 = cut[b + 1];
+        double *buf = d_p + (b & 1) * full_rows * n_pairs;
         if (b >= 2) SD_TRY(cudaStreamWaitEvent(s_k, ev[2 * (b - 2) + 1], 0));   // buffer drained
-        sd::FisherParams p{};
+        FisherParams p{};
         p.n_junctions = J; p.n_samples = n_samples;
-        p.inc = d_inc; p.ld_inc = n_samples; p.exc = d_exc; p.ld_exc = n_samples;
+        p.inc = d_inc; p.ld_inc = ldd; p.exc = d_exc; p.ld_exc = ldd;
         p.n_pairs = n_pairs; p.pair_a = d_pa; p.pair_b = d_pb;
         p.p_out = buf - r0 * n_pairs; p.ld_p = n_pairs; p.row_begin = r0; p.row_end = r1;
-        rc = sd::launch_fisher_pairwise(p, s_k, max_cell);
+        rc = launch_fisher_pairwise(p, s_k, max_cell);
         if (rc != SD_OK) { cleanup(); return rc; }
         SD_TRY(cudaEventRecord(ev[2 * b], s_k));
         SD_TRY(cudaStreamWaitEvent(s_out, ev[2 * b], 0));
@@ -774,6 +801,38 @@ int sd_fisher_pairwise_host(int device, int64_t n_junctions, int32_t n_samples, 
 #undef SD_TRY
     cleanup();
     return SD_OK;
+}
+
+}  // namespace sd
+
+extern "C" {
+
+// Host-buffer form: inc / exc / pairs / p_out are HOST pointers.
+int sd_fisher_pairwise_host(int device, int64_t n_junctions, int32_t n_samples, const int32_t *inc,
+                            int64_t ld_inc, const int64_t *exc, int64_t ld_exc, int64_t n_pairs,
+                            const int32_t *pair_a, const int32_t *pair_b, double *p_out, int64_t ld_p)
+{
+    SD_REQUIRE(n_junctions >= 0 && n_samples >= 0 && n_pairs >= 0, "sd_fisher_pairwise_host: negative size");
+    if (n_junctions == 0 || n_pairs == 0) return SD_OK;
+    SD_REQUIRE(inc && exc && pair_a && pair_b && p_out, "sd_fisher_pairwise_host: null pointer");
+    SD_REQUIRE(ld_inc >= n_samples && ld_exc >= n_samples && ld_p >= n_pairs,
+               "sd_fisher_pairwise_host: ld too small");
+    return sd::pairwise_host_impl("sd_fisher_pairwise_host", device, n_junctions, n_samples, inc, ld_inc, exc, ld_exc, nullptr,
+                                  nullptr, n_pairs, pair_a, pair_b, p_out, ld_p);
+}
+
+// The whole pairwise hot loop for host buffers (pairwise_fisher.py:154-180): inclusion counts and the
+// cluster CSR in, p-values out; the exclusion counts never exist on the host.
+int sd_pairwise_host(int device, int64_t n_junctions, int32_t n_samples, const int32_t *inc, int64_t ld_inc,
+                     const int32_t *row_ptr, const int32_t *col_idx, int64_t n_pairs, const int32_t *pair_a,
+                     const int32_t *pair_b, double *p_out, int64_t ld_p)
+{
+    SD_REQUIRE(n_junctions >= 0 && n_samples >= 0 && n_pairs >= 0, "sd_pairwise_host: negative size");
+    if (n_junctions == 0 || n_pairs == 0) return SD_OK;
+    SD_REQUIRE(inc && row_ptr && pair_a && pair_b && p_out, "sd_pairwise_host: null pointer");
+    SD_REQUIRE(ld_inc >= n_samples && ld_p >= n_pairs, "sd_pairwise_host: ld too small");
+    return sd::pairwise_host_impl("sd_pairwise_host", device, n_junctions, n_samples, inc, ld_inc, nullptr, 0, row_ptr, col_idx,
+                                  n_pairs, pair_a, pair_b, p_out, ld_p);
 }
 
 }  // extern "C"

@@ -190,7 +190,8 @@ struct HostPipe {
     std::vector<cudaEvent_t> events;
     uint16_t *ring = nullptr;          // pinned staging, kRingSlots slots
     size_t ring_slot_bytes = 0;
-    double ms_per_mb[2] = {0, 0};      // last large call as int32 [0] / uint16 [1]: the format autotuner
+    double ms_per_mb[2] = {0, 0};      // best large call as int32 [0] / uint16 [1]: the format autotuner
+    int tune_samples[2] = {0, 0};
     long tune_calls = 0;
 };
 HostPipe g_pipe[kMaxDevices];
@@ -318,7 +319,7 @@ int sd_quant_ps_host(int device, int64_t n_junctions, int32_t n_samples, const i
     // host threads slowed the copy-back stream and it took 40-42 ms against 35.7; with two ranks
     // sharing a host it loses outright (60 against 48.9 ms, which IS the two-GPU duplex ceiling).  So
     // the format is chosen by measurement: ranks of a multi-GPU job (LOCAL_WORLD_SIZE > 1) and small
-    // matrices send int32; otherwise the per-device context times its first large call in each
+    // matrices send int32; otherwise the per-device context times its first two large calls in each
     // format and keeps the faster one, trying the other again every 32nd call.  SD_QUANT_HOST_U16=0/1
     // overrides.  Results never depend on the format.
     HostPipe &hp = g_pipe[device];
@@ -333,8 +334,10 @@ int sd_quant_ps_host(int device, int64_t n_junctions, int32_t n_samples, const i
         if (alone && cells_mb >= 256.0) {
             tuning = true;
             ++hp.tune_calls;
-            if (hp.ms_per_mb[0] <= 0) use_u16 = false;
-            else if (hp.ms_per_mb[1] <= 0) use_u16 = true;
+            // two samples per format before deciding (a format's first call also pays first-use costs:
+            // module load, tensor-map entry point, the pinned ring), the better of the two counts
+            if (hp.tune_samples[0] < 2) use_u16 = false;
+            else if (hp.tune_samples[1] < 2) use_u16 = true;
             else {
                 use_u16 = hp.ms_per_mb[1] < hp.ms_per_mb[0];
                 if (hp.tune_calls % 32 == 0) use_u16 = !use_u16;          // look at the other format again
@@ -523,7 +526,13 @@ int sd_quant_ps_host(int device, int64_t n_junctions, int32_t n_samples, const i
 #undef SD_TRY_RC
     const auto t_enqueued = clk::now();
     cleanup();
-    if (tuning) hp.ms_per_mb[use_u16 ? 1 : 0] = std::chrono::duration<double, std::milli>(clk::now() - t_begin).count() / cells_mb;
+    if (tuning) {
+        const int m = use_u16 ? 1 : 0;
+        const double t = std::chrono::duration<double, std::milli>(clk::now() - t_begin).count() / cells_mb;
+        // keep the best of the first samples; later calls track the current speed of the chosen format
+        hp.ms_per_mb[m] = hp.tune_samples[m] == 1 ? std::min(hp.ms_per_mb[m], t) : t;
+        ++hp.tune_samples[m];
+    }
     if (debug)
         fprintf(stderr,
                 "[sd_quant_ps_host] %lld blocks of %lld rows, uint16 %s (%lld blocks sent as int32), %d workers: enqueue "

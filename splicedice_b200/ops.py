@@ -226,6 +226,24 @@ def fisher_pairwise_host(inc, exc, pair_a, pair_b, out=None, device=0):
     return out
 
 
+def pairwise_host(inc, row_ptr, col_idx, pair_a, pair_b, out=None, device=0):
+    """sd_pairwise_host: host inclusion counts + cluster CSR -> host p-values (exclusion counts are summed
+    on the device)."""
+    require_cuda()
+    inc = np.ascontiguousarray(inc, dtype=np.int32) if not isinstance(inc, torch.Tensor) else inc
+    J, S = inc.shape
+    rp = np.ascontiguousarray(row_ptr, dtype=np.int32)
+    ci = np.ascontiguousarray(col_idx, dtype=np.int32)
+    pa = np.ascontiguousarray(pair_a, dtype=np.int32)
+    pb = np.ascontiguousarray(pair_b, dtype=np.int32)
+    if out is None:
+        out = torch.empty((J, len(pa)), dtype=torch.float64)
+    ld = lambda t: t.stride(0) if isinstance(t, torch.Tensor) else t.strides[0] // t.itemsize  # noqa: E731
+    native.call("sd_pairwise_host", device, J, S, native.ptr(inc), ld(inc), native.ptr(rp), native.ptr(ci), len(pa),
+                native.ptr(pa), native.ptr(pb), native.ptr(out), ld(out))
+    return out
+
+
 BH_COLUMNS, BH_ALL = 0, 1
 _BH_MAX_VALUES = 2 ** 31 - 1
 

@@ -71,6 +71,16 @@ def test_pairwise_layout_and_exclusions():
     # host-buffer entry point, ragged row range
     got_h = ops.fisher_pairwise_host(counts, exc, pa, pb).numpy()
     np.testing.assert_array_equal(got_h, got)
+    # the whole hot loop for host buffers: exclusion counts summed on the device from the CSR
+    got_w = ops.pairwise_host(counts, csr["row_ptr"], csr["col_idx"], pa, pb).numpy()
+    np.testing.assert_array_equal(got_w, got)
+    wide = np.zeros((J, S + 5), dtype=np.int32)                   # strided host input, odd sample count
+    wide[:, :S] = counts
+    sub = torch.from_numpy(wide)[:, :S - 1]
+    pa2, pb2 = oracle_np.all_pairs(S - 1)
+    exc2 = oracle_np.exclusion_sums(counts[:, :S - 1], csr["row_ptr"], csr["col_idx"])
+    got_s = ops.pairwise_host(sub, csr["row_ptr"], csr["col_idx"], pa2, pb2).numpy()
+    _check(got_s.ravel(), fisher_c.pairwise(counts[:, :S - 1], exc2, pa2, pb2).ravel(), rtol=1e-11)
 
 
 def test_negative_entries_are_rejected():

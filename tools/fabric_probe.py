@@ -42,7 +42,7 @@ def main():
                 os.environ["SD_QUANT_HOST_BLOCK_MB"] = str(mb)
             ops.quant_ps_host(h_counts, rp, ci, out=h_ps, device=local)
             ts = []
-            for _ in range(5):
+            for _ in range(8):
                 torch.cuda.synchronize()
                 if world > 1:
                     dist.barrier()
