@@ -15,7 +15,8 @@
 // All ids written to row_ptr / col_idx are OUTPUT rows (tuple order (chrom, start, end, strand)).
 //
 // The output row order needs no sort of its own (k_out_rank).  Device-wide sort / scan primitives
-// are CUB's (two radix sorts for the cluster order, one for the prior lists, five scans); everything
+// are CUB's (one radix sort for the cluster order plus a fix-up of equal-key runs, one sort for the prior
+// lists over 2 log2(n) bits, six scans); everything
 // else is a kernel below.  One host synchronisation per call (nnz, component count, overflow check).
 #include <cub/cub.cuh>
 
@@ -43,6 +44,36 @@ __device__ __forceinline__ uint64_t seg_key(int32_t chrom, int32_t strand, int32
 __global__ void k_iota_end(int64_t n, const int32_t *end, uint32_t *key, int32_t *val)
 {
     SD_GRID_STRIDE(i, n) { key[i] = (uint32_t)end[i]; val[i] = (int32_t)i; }
+}
+// (chrom, strand, start) key of every junction in input order
+__global__ void k_key_direct(int64_t n, const int32_t *chrom, const int32_t *strand, const int32_t *start, uint64_t *key,
+                             int32_t *val)
+{
+    SD_GRID_STRIDE(i, n) { key[i] = seg_key(chrom[i], strand[i], start[i]); val[i] = (int32_t)i; }
+}
+// After ONE sort by (chrom, strand, start): junctions that share all three (a common donor site)
+// form short runs that still have to be ordered by `end`.  The thread at the head of a run sorts
+// it by insertion; a run longer than kMaxRun raises `flag` and the caller repeats the build with
+// the two-pass sort (end first, then the 64-bit key).
+constexpr int kMaxRun = 64;
+__global__ void k_fix_ties(int64_t n, const uint64_t *key_sorted, int32_t *order, const int32_t *end, int32_t *flag)
+{
+    SD_GRID_STRIDE(i, n)
+    {
+        const uint64_t key = key_sorted[i];
+        if ((i > 0 && key_sorted[i - 1] == key) || i + 1 >= n || key_sorted[i + 1] != key) continue;   // not the head of a run
+        int64_t j = i + 2;
+        while (j < n && j - i <= kMaxRun && key_sorted[j] == key) ++j;
+        const int len = (int)(j - i);
+        if (len > kMaxRun) { atomicExch(flag, 1); continue; }
+        for (int a = 1; a < len; ++a) {
+            const int32_t v = order[i + a];
+            const int32_t e = end[v];
+            int b = a - 1;
+            while (b >= 0 && end[order[i + b]] > e) { order[i + b + 1] = order[i + b]; --b; }
+            order[i + b + 1] = v;
+        }
+    }
 }
 __global__ void k_key_cluster(int64_t n, const int32_t *order, const int32_t *chrom, const int32_t *strand,
                               const int32_t *start, uint64_t *key)
@@ -120,8 +151,10 @@ struct SegMaxOp {
 
 // per position: later-neighbour run, segment heads, scan input, difference array
 __global__ void k_sweep(int64_t n, const int32_t *order, const uint64_t *key_sorted, const int32_t *chrom,
-                        const int32_t *strand, const int32_t *end, int32_t *n_later, int32_t *diff, SegMax *seg_in)
+                        const int32_t *strand, const int32_t *end, int32_t *n_later, int32_t *diff, SegMax *seg_in,
+                        unsigned long long *edges)
 {
+    unsigned long long my_edges = 0;
     SD_GRID_STRIDE(i, n)
     {
         const int32_t j = order[i];
@@ -134,6 +167,7 @@ __global__ void k_sweep(int64_t n, const int32_t *order, const uint64_t *key_sor
         }
         const int32_t later = (int32_t)(lo - 1 - i);
         n_later[i] = later;
+        my_edges += (unsigned long long)later;
         if (later > 0) {
             atomicAdd(diff + i + 1, 1);
             atomicAdd(diff + i + 1 + later, -1);
@@ -142,67 +176,65 @@ __global__ void k_sweep(int64_t n, const int32_t *order, const uint64_t *key_sor
         seg_in[i].head = head ? 1 : 0;
         seg_in[i].val = end[j];
     }
+    // 64-bit edge count of the whole build (the int32 CSR cannot hold more than 2^31 - 1 entries)
+    for (int o = 16; o; o >>= 1) my_edges += __shfl_xor_sync(0xffffffffu, my_edges, o);
+    if ((threadIdx.x & 31) == 0 && my_edges) atomicAdd(edges, my_edges);
 }
 
-// comp_head[k] = segment head, or the running max of `end` before k is below start_k
+// comp_head[k] = segment head, or the running max of `end` before k is below start_k; position 0 is
+// left at 0 so that the inclusive count of heads is the 0-based component id
 __global__ void k_comp_head(int64_t n, const uint64_t *key_sorted, const SegMax *seg_scan, int32_t *comp_head)
 {
     SD_GRID_STRIDE(i, n)
     {
         const bool head = i == 0 || (key_sorted[i] >> 31) != (key_sorted[i - 1] >> 31);
         const int32_t start = (int32_t)(key_sorted[i] & 0x7FFFFFFFu);
-        comp_head[i] = (head || seg_scan[i - 1].val < start) ? 1 : 0;
+        comp_head[i] = (i > 0 && (head || seg_scan[i - 1].val < start)) ? 1 : 0;
     }
-}
-__global__ void k_comp_id(int64_t n, int32_t *comp)   // inclusive count of heads -> 0-based id
-{
-    SD_GRID_STRIDE(i, n) comp[i] -= 1;
 }
 __global__ void k_degree(int64_t n, const int32_t *row_of_pos, const int32_t *n_prior, const int32_t *n_later,
                          int32_t *deg_row)
 {
     SD_GRID_STRIDE(i, n) deg_row[row_of_pos[i]] = n_prior[i] + n_later[i];
 }
-__global__ void k_edges(int64_t n, const int32_t *n_later, const int64_t *later_off, uint64_t *edge)
+// edge (k, b), b < k: key = k in the high bits, (mask - b) in the low `shift` bits, so that one
+// ascending sort over 2 * shift bits lists every k's priors most recent first
+__global__ void k_edges(int64_t n, int shift, const int32_t *n_later, const int64_t *later_off, uint64_t *edge)
 {
+    const uint64_t mask = (uint64_t(1) << shift) - 1;
     SD_GRID_STRIDE(i, n)
     {
         const int32_t m = n_later[i];
         uint64_t *dst = edge + later_off[i];
-        for (int32_t t = 0; t < m; ++t)
-            dst[t] = ((uint64_t)(uint32_t)(i + 1 + t) << 32) | (uint64_t)(0xFFFFFFFFu - (uint32_t)i);
+        for (int32_t t = 0; t < m; ++t) dst[t] = ((uint64_t)(i + 1 + t) << shift) | (mask - (uint64_t)i);
     }
 }
-__global__ void k_fill(int64_t n, const int32_t *row_of_pos, const int32_t *row_ptr, const int32_t *n_prior,
+__global__ void k_fill(int64_t n, int shift, const int32_t *row_of_pos, const int32_t *row_ptr, const int32_t *n_prior,
                        const int32_t *n_later, const int64_t *prior_off, const uint64_t *edge_sorted,
                        int32_t *col_idx)
 {
+    const uint64_t mask = (uint64_t(1) << shift) - 1;
     SD_GRID_STRIDE(k, n)
     {
         int32_t *dst = col_idx + row_ptr[row_of_pos[k]];
         const int32_t np = n_prior[k], nl = n_later[k];
         const uint64_t *src = edge_sorted + prior_off[k];
-        for (int32_t t = 0; t < np; ++t) dst[t] = row_of_pos[0xFFFFFFFFu - (uint32_t)(src[t] & 0xFFFFFFFFu)];
+        for (int32_t t = 0; t < np; ++t) dst[t] = row_of_pos[mask - (src[t] & mask)];
         for (int32_t t = 0; t < nl; ++t) dst[np + t] = row_of_pos[k + 1 + t];
     }
 }
-__global__ void k_sum64(int64_t n, const int32_t *in, unsigned long long *out)
-{
-    unsigned long long acc = 0;
-    SD_GRID_STRIDE(i, n) acc += (unsigned long long)in[i];
-    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
-}
-__global__ void k_widen(int64_t n, const int32_t *in, int64_t *out)
-{
-    SD_GRID_STRIDE(i, n) out[i] = in[i];
-}
+// int32 counts read as int64 by the offset scans (element n, one past the counts, reads as 0)
+struct WidenCount {
+    const int32_t *in;
+    int64_t n;
+    __device__ __forceinline__ int64_t operator()(int64_t i) const { return i < n ? (int64_t)in[i] : 0; }
+};
 
 inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 // carve-up of the build workspace
 struct BuildWs {
-    size_t key_a, key_b, val_a, val_b, n_later, n_prior, diff, seg, deg_row, cub, total;
+    size_t key_a, key_b, val_a, val_b, n_later, n_prior, diff, seg, deg_row, misc, cub, total;
     size_t cub_bytes;
 };
 
@@ -238,6 +270,7 @@ int layout_build(int64_t n, BuildWs *w)
     w->diff = take((size_t)(n + 1) * 4);
     w->seg = take((size_t)n * sizeof(SegMax) * 2);
     w->deg_row = take((size_t)(n + 1) * 4);
+    w->misc = take(256);                      // [0] long-run flag (int32), [8] edge count (uint64)
     if (int rc = cub_bytes_build(n, &w->cub_bytes)) return rc;
     w->cub = take(w->cub_bytes);
     w->total = off;
@@ -259,7 +292,11 @@ int layout_fill(int64_t n, int64_t nnz, FillWs *w)
     w->edge_b = take((size_t)std::max<int64_t>(e, 1) * 8);
     size_t b1 = 0, b2 = 0;
     SD_CHECK_CUDA((cub::DeviceRadixSort::SortKeys<uint64_t>(nullptr, b1, nullptr, nullptr, (int)std::max<int64_t>(e, 1))));
-    SD_CHECK_CUDA((cub::DeviceScan::ExclusiveSum<const int64_t *, int64_t *>(nullptr, b2, nullptr, nullptr, (int)(n + 1))));
+    {
+        cub::CountingInputIterator<int64_t> idx(0);
+        cub::TransformInputIterator<int64_t, WidenCount, cub::CountingInputIterator<int64_t>> in(idx, WidenCount{nullptr, n});
+        SD_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, b2, in, (int64_t *)nullptr, (int)(n + 1)));
+    }
     w->cub_bytes = std::max(b1, b2);
     w->cub = take(w->cub_bytes);
     w->total = off;
@@ -326,48 +363,58 @@ int sd_cluster_build(int64_t n, const int32_t *chrom_rank, const int32_t *strand
     const int g = grid_for(n);
     const int ni = (int)n;
 
-    // ---- cluster order: stable LSD sort, end then (chrom, strand, start) ------------------
-    uint32_t *key32_a = (uint32_t *)key_a, *key32_b = (uint32_t *)key_b;
-    k_iota_end<<<g, kBlock, 0, stream>>>(n, end, key32_a, val_a);
-    SD_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(cub_ws, cub_b, key32_a, key32_b, val_a, val_b, ni, 0, 32, stream));
-    k_key_cluster<<<g, kBlock, 0, stream>>>(n, val_b, chrom_rank, strand_rank, start, key_a);
-    SD_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(cub_ws, cub_b, key_a, key_b, val_b, cluster_order, ni, 0, 64, stream));
-    // key_b = sorted (chrom, strand, start) keys
-    // ---- output row order from the cluster order (merge ranks, no sort) --------------------
-    k_out_rank<<<g, kBlock, 0, stream>>>(n, cluster_order, key_b, end, out_row, row_of_pos);
-
-    // ---- sweep ----------------------------------------------------------------------------
-    SD_CHECK_CUDA(cudaMemsetAsync(diff, 0, (size_t)(n + 1) * 4, stream));
-    k_sweep<<<g, kBlock, 0, stream>>>(n, cluster_order, key_b, chrom_rank, strand_rank, end, n_later, diff, seg_in);
-    SD_CHECK_CUDA(cub::DeviceScan::InclusiveSum(cub_ws, cub_b, (const int32_t *)diff, n_prior, ni + 1, stream));
-    SD_CHECK_CUDA(cub::DeviceScan::InclusiveScan(cub_ws, cub_b, (const SegMax *)seg_in, seg_out, SegMaxOp(), ni, stream));
-    k_comp_head<<<g, kBlock, 0, stream>>>(n, key_b, seg_out, val_a);
-    SD_CHECK_CUDA(cub::DeviceScan::InclusiveSum(cub_ws, cub_b, (const int32_t *)val_a, comp_id, ni, stream));
-    k_comp_id<<<g, kBlock, 0, stream>>>(n, comp_id);
-
-    // 64-bit edge count (the int32 CSR cannot hold more than 2^31 - 1 entries): read back together
-    // with nnz and the component count in the call's single synchronisation -- an overflowing
-    // prefix sum below only produces garbage that is never returned
-    unsigned long long *d_edges = (unsigned long long *)diff;      // diff is dead after the prefix sum
-    SD_CHECK_CUDA(cudaMemsetAsync(d_edges, 0, 8, stream));
-    k_sum64<<<g, kBlock, 0, stream>>>(n, n_later, d_edges);
-
-    // ---- CSR row pointer in output-row space -----------------------------------------------
-    SD_CHECK_CUDA(cudaMemsetAsync(deg_row + n, 0, 4, stream));
-    k_degree<<<g, kBlock, 0, stream>>>(n, row_of_pos, n_prior, n_later, deg_row);
-    SD_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(cub_ws, cub_b, (const int32_t *)deg_row, row_ptr, ni + 1, stream));
-    if (int rc = check_launch("sd_cluster_build kernels")) return rc;
-
+    int32_t *d_flag = (int32_t *)(ws + w.misc);
+    unsigned long long *d_edges = (unsigned long long *)(ws + w.misc + 8);
     unsigned long long h_edges = 0;
-    int32_t h_nnz = 0, h_comp = 0;
-    SD_CHECK_CUDA(cudaMemcpyAsync(&h_edges, d_edges, 8, cudaMemcpyDeviceToHost, stream));
-    SD_CHECK_CUDA(cudaMemcpyAsync(&h_nnz, row_ptr + n, 4, cudaMemcpyDeviceToHost, stream));
-    SD_CHECK_CUDA(cudaMemcpyAsync(&h_comp, comp_id + (n - 1), 4, cudaMemcpyDeviceToHost, stream));
-    SD_CHECK_CUDA(cudaStreamSynchronize(stream));
+    int32_t h_nnz = 0, h_comp = 0, h_flag = 0;
+    // First attempt: ONE radix sort by (chrom, strand, start) and a fix-up of the short runs that
+    // share all three; a run longer than kMaxRun (seen at the final read-back) repeats the build
+    // with the two-pass sort.
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        SD_CHECK_CUDA(cudaMemsetAsync(ws + w.misc, 0, 16, stream));
+        if (attempt == 0) {
+            k_key_direct<<<g, kBlock, 0, stream>>>(n, chrom_rank, strand_rank, start, key_a, val_a);
+            SD_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(cub_ws, cub_b, key_a, key_b, val_a, cluster_order, ni, 0, 64, stream));
+            k_fix_ties<<<g, kBlock, 0, stream>>>(n, key_b, cluster_order, end, d_flag);
+        } else {
+            // stable LSD sort, end then (chrom, strand, start)
+            uint32_t *key32_a = (uint32_t *)key_a, *key32_b = (uint32_t *)key_b;
+            k_iota_end<<<g, kBlock, 0, stream>>>(n, end, key32_a, val_a);
+            SD_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(cub_ws, cub_b, key32_a, key32_b, val_a, val_b, ni, 0, 32, stream));
+            k_key_cluster<<<g, kBlock, 0, stream>>>(n, val_b, chrom_rank, strand_rank, start, key_a);
+            SD_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(cub_ws, cub_b, key_a, key_b, val_b, cluster_order, ni, 0, 64, stream));
+        }
+        // key_b = sorted (chrom, strand, start) keys
+        // ---- output row order from the cluster order (merge ranks, no sort) --------------------
+        k_out_rank<<<g, kBlock, 0, stream>>>(n, cluster_order, key_b, end, out_row, row_of_pos);
+
+        // ---- sweep ----------------------------------------------------------------------------
+        SD_CHECK_CUDA(cudaMemsetAsync(diff, 0, (size_t)(n + 1) * 4, stream));
+        k_sweep<<<g, kBlock, 0, stream>>>(n, cluster_order, key_b, chrom_rank, strand_rank, end, n_later, diff, seg_in, d_edges);
+        SD_CHECK_CUDA(cub::DeviceScan::InclusiveSum(cub_ws, cub_b, (const int32_t *)diff, n_prior, ni + 1, stream));
+        SD_CHECK_CUDA(cub::DeviceScan::InclusiveScan(cub_ws, cub_b, (const SegMax *)seg_in, seg_out, SegMaxOp(), ni, stream));
+        k_comp_head<<<g, kBlock, 0, stream>>>(n, key_b, seg_out, val_a);
+        SD_CHECK_CUDA(cub::DeviceScan::InclusiveSum(cub_ws, cub_b, (const int32_t *)val_a, comp_id, ni, stream));
+
+        // ---- CSR row pointer in output-row space -----------------------------------------------
+        SD_CHECK_CUDA(cudaMemsetAsync(deg_row + n, 0, 4, stream));
+        k_degree<<<g, kBlock, 0, stream>>>(n, row_of_pos, n_prior, n_later, deg_row);
+        SD_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(cub_ws, cub_b, (const int32_t *)deg_row, row_ptr, ni + 1, stream));
+        if (int rc = check_launch("sd_cluster_build kernels")) return rc;
+
+        // the call's single synchronisation: long-run flag, 64-bit edge count (an overflowing prefix
+        // sum above only produces garbage that is never returned), nnz, component count
+        SD_CHECK_CUDA(cudaMemcpyAsync(&h_flag, d_flag, 4, cudaMemcpyDeviceToHost, stream));
+        SD_CHECK_CUDA(cudaMemcpyAsync(&h_edges, d_edges, 8, cudaMemcpyDeviceToHost, stream));
+        SD_CHECK_CUDA(cudaMemcpyAsync(&h_nnz, row_ptr + n, 4, cudaMemcpyDeviceToHost, stream));
+        SD_CHECK_CUDA(cudaMemcpyAsync(&h_comp, comp_id + (n - 1), 4, cudaMemcpyDeviceToHost, stream));
+        SD_CHECK_CUDA(cudaStreamSynchronize(stream));
+        if (!h_flag) break;
+    }
     if (2 * h_edges > 0x7FFFFFFFull)
         return fail(SD_ERR_OVERFLOW, "sd_cluster_build: %llu adjacency entries do not fit int32 indices", 2 * h_edges);
     *nnz_host = h_nnz;
-    *n_components_host = (int64_t)h_comp + 1;
+    *n_components_host = (int64_t)h_comp + 1;            // comp_id is 0-based
     return SD_OK;
 }
 
@@ -397,15 +444,17 @@ int sd_cluster_fill(int64_t n, int64_t nnz, const int32_t *row_of_pos, const int
     const int g = grid_for(n);
     const int64_t e = nnz / 2;
 
-    k_widen<<<g, kBlock, 0, stream>>>(n, n_later, later_off);
-    SD_CHECK_CUDA(cudaMemsetAsync(later_off + n, 0, 8, stream));
-    SD_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(cub_ws, cub_b, (const int64_t *)later_off, later_off, (int)(n + 1), stream));
-    k_widen<<<g, kBlock, 0, stream>>>(n, n_prior, prior_off);
-    SD_CHECK_CUDA(cudaMemsetAsync(prior_off + n, 0, 8, stream));
-    SD_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(cub_ws, cub_b, (const int64_t *)prior_off, prior_off, (int)(n + 1), stream));
-    k_edges<<<g, kBlock, 0, stream>>>(n, n_later, later_off, edge_a);
-    SD_CHECK_CUDA(cub::DeviceRadixSort::SortKeys(cub_ws, cub_b, edge_a, edge_b, (int)e, 0, 32 + bits_for(n), stream));
-    k_fill<<<g, kBlock, 0, stream>>>(n, row_of_pos, row_ptr, n_prior, n_later, prior_off, edge_b, col_idx);
+    const int shift = bits_for(n + 1);
+    {
+        cub::CountingInputIterator<int64_t> idx(0);
+        cub::TransformInputIterator<int64_t, WidenCount, cub::CountingInputIterator<int64_t>> later_in(idx, WidenCount{n_later, n});
+        cub::TransformInputIterator<int64_t, WidenCount, cub::CountingInputIterator<int64_t>> prior_in(idx, WidenCount{n_prior, n});
+        SD_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(cub_ws, cub_b, later_in, later_off, (int)(n + 1), stream));
+        SD_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(cub_ws, cub_b, prior_in, prior_off, (int)(n + 1), stream));
+    }
+    k_edges<<<g, kBlock, 0, stream>>>(n, shift, n_later, later_off, edge_a);
+    SD_CHECK_CUDA(cub::DeviceRadixSort::SortKeys(cub_ws, cub_b, edge_a, edge_b, (int)e, 0, 2 * shift, stream));
+    k_fill<<<g, kBlock, 0, stream>>>(n, shift, row_of_pos, row_ptr, n_prior, n_later, prior_off, edge_b, col_idx);
     return check_launch("sd_cluster_fill kernels");
 }
 

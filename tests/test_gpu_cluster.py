@@ -114,3 +114,23 @@ def test_dense_small_coordinates_and_three_strand_labels(seed):
     for j, lst in adj.items():
         brute = {k for k in js if k != j and k[0] == j[0] and k[3] == j[3] and k[1] <= j[2] and j[1] <= k[2]}
         assert set(lst) == brute and len(lst) == len(brute)
+
+
+@pytest.mark.parametrize("run", [2, 64, 65, 400])
+def test_runs_of_junctions_sharing_a_start(run):
+    """The cluster order comes from ONE sort by (chrom, strand, start) plus a fix-up of the runs that
+    share all three; runs of up to 64 are sorted in place, a longer one makes the build repeat with
+    the two-pass sort.  Both sides of that limit, several runs per set, against the oracle."""
+    rng = np.random.default_rng(run)
+    js = set()
+    for k, (chrom, strand) in enumerate([("chr1", "+"), ("chr1", "-"), ("chr2", "+")]):
+        start = 1000 + 7 * k
+        for e in rng.choice(np.arange(start + 50, start + 50 + 3 * run), size=run, replace=False):
+            js.add((chrom, start, int(e), strand))
+        for _ in range(40):                                        # clutter around the runs
+            a = int(rng.integers(900, 1400))
+            js.add((chrom, a, a + int(rng.integers(50, 400)), strand))
+    js = list(js)
+    rng.shuffle(js)
+    c, s, st, en, _, _ = oracle_np.junctions_to_arrays(js)
+    _compare((c, s, st, en))
