@@ -153,3 +153,19 @@ def test_exp_small_against_long_double(twin):
     assert (twin.exp_small(np.array([-746.5, -800.0, -1e308, -np.inf])) == 0.0).all()
     sub = twin.exp_small(np.array([-720.0, -740.0, -745.0]))
     assert (sub > 0).all() and np.allclose(sub, np.exp(np.array([-720.0, -740.0, -745.0])), rtol=1e-6, atol=5e-324)
+
+
+TIE_RULE_TABLES = [[20000, 19998, 20000, 20002], [20002, 19998, 20000, 20000], [60003, 59997, 60000, 60000]]
+
+
+def test_tie_rule_is_the_modern_scipy_one(twin):
+    """Observed count next to the mode with pmf(observed) within 1e-4 -- but not within 1e-14 -- of
+    pmf(mode): scipy >= 1.9 (window 1e-14, stats/_stats_py.py:5082-5086; the image's 1.18.1) sums the
+    tails (p ~ 0.994); the scipy 1.4.1 the reference pins returned exactly 1 here (window 1e-4).  The
+    kernel arithmetic follows the modern rule, and DESIGN.md section 2 says so."""
+    from scipy.stats import fisher_exact
+    t = np.array(TIE_RULE_TABLES)
+    want = np.array([fisher_exact([[a, b], [c, d]])[1] for a, b, c, d in t.tolist()])
+    assert (want < 0.999).all()
+    assert _max_rel(twin(t), want) < 1e-9
+    np.testing.assert_allclose(twin(t), fisher_c.fisher_two_sided(t[:, 0], t[:, 1], t[:, 2], t[:, 3]), rtol=1e-11)

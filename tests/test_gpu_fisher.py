@@ -220,3 +220,16 @@ def test_totals_straddling_the_table_cap():
     gotp = ops.fisher_pairwise(torch.from_numpy(inc).to(dev), torch.from_numpy(exc).to(dev), pa, pb).cpu().numpy()
     _check(gotp.ravel(), wantp.ravel())
     np.testing.assert_array_equal(gotp[:, 0], got)
+
+
+def test_tie_rule_is_the_modern_scipy_one():
+    """See tests/test_fisher_twin.py: tables where scipy 1.4.1's 1e-4 tie window would return exactly 1
+    and scipy >= 1.9 does not; the kernel follows the latter."""
+    from scipy.stats import fisher_exact
+    from tests.test_fisher_twin import TIE_RULE_TABLES
+    _, ops = _ops()
+    t = np.array(TIE_RULE_TABLES)
+    want = np.array([fisher_exact([[a, b], [c, d]])[1] for a, b, c, d in t.tolist()])
+    got = ops.fisher_tables(t[:, 0], t[:, 1], t[:, 2], t[:, 3]).cpu().numpy()
+    assert (got < 0.999).all()
+    _check(got, want)
