@@ -952,8 +952,10 @@ def main():
                                           "run inside the timed bench)") if traffic else None,
                          "kernel": kernel_name, "kernel_ms": kernel_ms,
                          "bytes_per_cell": 8, "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
-            "gpu_launches_note": f"{args.steps} in the headline timed region; the rest in the variant / Fisher / strong / configs[3] regions",
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps,
+            "gpu_launches_all_timed_regions": launches,
+            "gpu_launches_note": f"{args.steps} quant kernel launches in the headline timed region (one per step); "
+                                 f"{launches} counting the variant / Fisher / strong-scaling / configs[3] timed regions too",
             "launch_mode": "cuda graph of K kernel launches" if graphed else "K stream launches",
             "clocks": clocks, "variants": variants, "fisher": fisher, "strong": strong, "collectives": collectives,
             "tcga": tcga,
