@@ -836,7 +836,7 @@ def main():
                 t_nccl = max_over_ranks(timed_calls(nccl_path, 5))
                 launches += 10
                 fused = {"what": "distributed.pairwise_fused: Fisher with peer-memory scatter stores + barrier + sd_bh_adjust in "
-                                 "place + strided peer copies back, against Fisher + NCCL all_to_all + sd_bh_adjust + all_to_all "
+                                 "place + one kernel of peer stores back, against Fisher + NCCL all_to_all + sd_bh_adjust + all_to_all "
                                  "(both: the whole per-slab pairwise step incl. Fisher)",
                          "fused_whole_ms": t_fused, "nccl_whole_ms": t_nccl, "speedup": t_nccl / t_fused,
                          "rows_bits_equal_one_gpu": all_true(same_fused)}
