@@ -14,6 +14,7 @@
 // FP64-pipe / issue bound: 7 FP64 instructions per summed tail term, no division or exp in the
 // loop, cut and rescale tests on the exponent words with integer instructions.
 #include <algorithm>
+#include <chrono>
 #include <mutex>
 #include <vector>
 
@@ -695,6 +696,9 @@ static int pairwise_host_impl(const char *who, int device, int64_t J, int32_t n_
             if (col_idx[k] < 0 || col_idx[k] >= J)
                 return fail(SD_ERR_INVALID, "%s: col_idx[%lld] = %d out of range", who, (long long)k, col_idx[k]);
     }
+    const bool debug = getenv("SD_HOST_PIPE_DEBUG") != nullptr;
+    using clk = std::chrono::steady_clock;
+    const auto t_begin = clk::now();
     int prev_dev = 0;
     SD_CHECK_CUDA(cudaGetDevice(&prev_dev));
     SD_CHECK_CUDA(cudaSetDevice(device));
@@ -775,6 +779,7 @@ static int pairwise_host_impl(const char *who, int device, int64_t J, int32_t n_
         rc = fisher_max_cell(all, s_k, &max_cell);
         if (rc != SD_OK) { cleanup(); return rc; }
     }
+    const auto t_scanned = clk::now();
     ev.resize((size_t)2 * n_blocks, nullptr);
     for (auto &e : ev) SD_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (int64_t b = 0; b < n_blocks; ++b) {
@@ -797,9 +802,17 @@ static int pairwise_host_impl(const char *who, int device, int64_t J, int32_t n_
                                      (size_t)(r1 - r0), cudaMemcpyDeviceToHost, s_out));
         SD_TRY(cudaEventRecord(ev[2 * b + 1], s_out));
     }
+    const auto t_enqueued = clk::now();
     SD_TRY(cudaStreamSynchronize(s_out));
 #undef SD_TRY
+    const auto t_done = clk::now();
     cleanup();
+    if (debug) {
+        auto ms = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        fprintf(stderr, "[%s] %lld blocks: upload + exclusions + max scan %.2f ms, enqueue %.2f ms, drain %.2f ms, cleanup %.2f ms\n",
+                who, (long long)n_blocks, ms(t_begin, t_scanned), ms(t_scanned, t_enqueued), ms(t_enqueued, t_done),
+                ms(t_done, clk::now()));
+    }
     return SD_OK;
 }
 
